@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for clipb200.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload embed|search]
+
+One "step" is one pass of a hot path over one batch of synthetic input:
+
+  embed  (BASELINE configs[1], the headline): preprocess + CLIP ViT-B/32 encode_image +
+         L2-normalise of one batch of 256 synthetic 224x224 uint8 images per GPU.
+         metric = images/sec; weak scaling (batch 256 per rank, no collective).
+  search (BASELINE configs[2]): one exact top-100 query over a 10M x 512 fp16 database
+         sharded over the N GPUs (scan + one NCCL gather + merge).  metric = queries/sec;
+         strong scaling (the database is fixed at 10M rows).
+
+`value` is timed on the device with CUDA events with inputs already resident in HBM;
+`e2e` is the same metric through the host-buffer public API (H2D/D2H inside the timed
+region).  `roofline` is computed for the dominant kernel from its live CUDA-event
+duration.  `cpu_baseline` times the CPU oracle port on a bounded sample (rank 0, N=1).
+`--impl reference` times the CPU restatement of the reference path on the host cores
+(the reference's own stack -- openai/CLIP + faiss-cpu -- is not installable offline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "cli-p_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+DB_ROWS = 10_000_000
+DIM = 512
+TOPK = 100
+EMBED_BATCH = 256
+GFLOP_PER_IMAGE = 8.8176          # SURVEY.md 8a, vision tower total
+SEARCH_BYTES_PER_ROW = 1024       # 512 x fp16, streamed once per query batch
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# =====================================================================================
+# distributed plumbing
+# =====================================================================================
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def timed_region(torch, dist, world, fn, steps, warmup, sampler=None):
+    """W untimed steps, then exactly K steps between barrier+sync, CUDA events on the
+    current stream, MAX over ranks.  Returns seconds."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / 1e3
+
+
+def timed_region_wall(torch, dist, world, fn, steps, warmup):
+    """Same bracket, host clock (for the synchronous host-buffer API)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return dt
+
+
+# =====================================================================================
+# search workload
+# =====================================================================================
+
+def cpu_search_baseline(seconds_budget: float = 12.0):
+    """Oracle port (oracle/flatip_ref.c: faiss's dot-product + heap algorithm restated,
+    OpenMP over rows) on a 1M-row fp16 slice, all host threads; scaled to 10M rows."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_build", "liboracle_flatip.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(so)
+    from clipb200 import synth
+    n = 1_000_000
+    xb = synth.unit_rows(n, seed=1000).astype(np.float16)
+    xq = synth.unit_rows(1, seed=7)
+    D = np.empty((1, TOPK), np.float32)
+    I = np.empty((1, TOPK), np.int64)
+
+    def one():
+        rc = lib.oracle_flatip_search(C.c_void_p(xb.ctypes.data), 1, C.c_int64(n), DIM, C.c_void_p(xq.ctypes.data),
+                                      C.c_int64(1), C.c_int64(TOPK), C.c_void_p(D.ctypes.data),
+                                      C.c_void_p(I.ctypes.data), 0)
+        assert rc == 0
+    one()
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        one()
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_budget or reps >= 200:
+            break
+    per_1m = dt / reps
+    qps_10m = 1.0 / (per_1m * (DB_ROWS / n))
+    return {"value": qps_10m, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{reps} single-query top-{TOPK} scans of a 1M x 512 fp16 slice "
+                      f"({per_1m * 1e3:.1f} ms each), scaled x{DB_ROWS // n} to 10M rows; "
+                      "oracle/flatip_ref.c (faiss IndexFlatIP algorithm restated; faiss-cpu is not installable offline)"}
+
+
+def run_search(args, torch, dist, rank, world, local):
+    from clipb200 import _native, faiss, sharded, synth
+    import ctypes as C
+    dev = torch.device("cuda", local)
+    lo, hi = sharded.shard_range(DB_ROWS, rank, world)
+    rows = synth.device_unit_rows(hi - lo, DIM, seed=1000 + rank, device=dev, dtype=torch.float16)
+    index = faiss.IndexFlatIP(DIM, storage="f16", devices=[local])
+    index.reserve(hi - lo)
+    index.add_device(rows)
+    del rows
+    torch.cuda.synchronize()
+    ds = sharded.DistributedFlatIP(index=index, device=dev)
+    ds.finalize()
+    q = synth.device_unit_rows(1, DIM, seed=7, device=dev, dtype=torch.float32)
+    q_host = q.cpu().pin_memory()
+    handle = index._shards[0].handle
+
+    def step_dev():
+        ds.search(q, TOPK)
+
+    out_host = {}
+
+    def step_e2e():
+        qd = q_host.to(dev, non_blocking=True)
+        D, I = ds.search(qd, TOPK)
+        if rank == 0:
+            out_host["D"], out_host["I"] = D.cpu(), I.cpu()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    _native.launch_count(reset=True)
+    N = _native.lib()
+    # warm up first, then switch kernel timing on for the timed steps only
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    N.cb_flatip_timing(handle, 1)
+    _native.launch_count(reset=True)
+    secs = timed_region(torch, dist, world, step_dev, args.steps, 0, sampler)
+    launches = _native.launch_count()
+    tot_ms, cnt = C.c_double(0), C.c_int(0)
+    N.cb_flatip_timing_read(handle, C.byref(tot_ms), C.byref(cnt))
+    N.cb_flatip_timing(handle, 0)
+    clocks = sampler.stop() if sampler else None
+    e2e_secs = timed_region_wall(torch, dist, world, step_e2e, args.steps, args.warmup)
+
+    peaks = load_peaks()
+    res = {
+        "metric": "queries/sec top-100 over 10M x 512 flat IP",
+        "value": args.steps / secs, "unit": "queries/s",
+        "ms_per_step": secs / args.steps * 1e3,
+        "scaling": "strong", "dtype": "f32 accumulate over f16 rows",
+        "config": {"workload": "exact IP search over 10M x 512 fp16 vectors, k=100, single query "
+                               "(BASELINE configs[2]), database sharded over the GPUs",
+                   "rows_total": DB_ROWS, "rows_per_gpu": hi - lo, "k": TOPK, "nq": 1,
+                   "l2": "inputs larger than L2 (>= 1.28 GB per GPU per step)"},
+        "e2e": {"value": args.steps / e2e_secs, "unit": "queries/s",
+                "h2d_bytes_per_step": DIM * 4, "d2h_bytes_per_step": TOPK * 12},
+        "gpu_launches": int(launches),
+    }
+    if cnt.value:
+        scan_s = tot_ms.value / 1e3 / cnt.value
+        ach = (hi - lo) * SEARCH_BYTES_PER_ROW / scan_s / 1e9
+        res["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                           "kernel": "flatip_scan_kernel<1,f16>", "kernel_ms": scan_s * 1e3,
+                           "peak_source": peaks["source"] + " (copy bandwidth)"}
+    return res, clocks
+
+
+def run_search_reference(args):
+    """--impl reference: the CPU restatement timed per step on a bounded sample."""
+    b = cpu_search_baseline(seconds_budget=max(2.0, 0.5 * (args.steps + args.warmup)))
+    return b
+
+
+# =====================================================================================
+# embed workload (filled in by clipb200.clip once the vision tower is built)
+# =====================================================================================
+
+def embed_available() -> bool:
+    try:
+        from clipb200 import clip  # noqa: F401
+        return hasattr(clip, "bench_hooks")
+    except Exception:
+        return False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=["embed", "search"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    workload = args.workload or ("embed" if embed_available() else "search")
+    if args.steps is None:
+        args.steps = 20 if workload == "embed" else 200
+    if args.warmup is None:
+        args.warmup = 5 if workload == "embed" else 20
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        if workload == "search":
+            b = run_search_reference(args)
+            metric = "queries/sec top-100 over 10M x 512 flat IP"
+            cfg = {"workload": "exact IP search over 10M x 512 fp16 vectors, k=100, single query (BASELINE configs[2])"}
+        else:
+            from clipb200 import clip
+            b, metric, cfg = clip.bench_hooks()["reference"](args)
+        line = {"impl": "reference", "metric": metric, "value": b["value"], "unit": b["unit"],
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak" if workload == "embed" else "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": b,
+                "e2e": {"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device -- clipb200 has no CPU path (use --impl reference for the CPU arm)",
+              file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        if workload == "search":
+            res, clocks = run_search(args, torch, dist, rank, world, local)
+        else:
+            from clipb200 import clip
+            res, clocks = clip.bench_hooks()["run"](args, torch, dist, rank, world, local, ClockSampler,
+                                                    timed_region, timed_region_wall, load_peaks)
+        if rank == 0:
+            line = {"metric": res.pop("metric"), "value": res.pop("value"), "unit": res.pop("unit"),
+                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True,
+                    "scaling": res.pop("scaling"), "vs_baseline": None, "dtype": res.pop("dtype"),
+                    "data": "synthetic", "config": res.pop("config")}
+            line.update(res)
+            line["clocks"] = clocks
+            if world == 1 and not args.no_cpu_baseline:
+                if workload == "search":
+                    line["cpu_baseline"] = cpu_search_baseline()
+                else:
+                    from clipb200 import clip
+                    line["cpu_baseline"] = clip.bench_hooks()["cpu_baseline"]()
+            print(json.dumps(line))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,89 @@
+"""ctypes binding of libclipb200.so (the C ABI declared in include/clipb200.h).
+
+There is deliberately no fallback: if the shared library is missing or fails to
+load, importing a symbol raises -- the product path never routes through the CPU
+oracle (that lives under oracle/ and is test infrastructure only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclipb200.so")
+
+CB_OK, CB_ERR_INVALID, CB_ERR_CUDA, CB_ERR_NOGPU, CB_ERR_OOM, CB_ERR_IO = range(6)
+CB_F32, CB_F16 = 0, 1
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libclipb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+
+# name -> (restype, argtypes); mirrors include/clipb200.h one to one
+SIGNATURES = {
+    "cb_last_error": (C.c_char_p, []),
+    "cb_abi_version": (_int, []),
+    "cb_device_count": (_int, [C.POINTER(_int)]),
+    "cb_launch_count": (_i64, [_int]),
+    "cb_flatip_create": (_int, [_int, _int, _int, C.POINTER(_p)]),
+    "cb_flatip_free": (None, [_p]),
+    "cb_flatip_ntotal": (_i64, [_p]),
+    "cb_flatip_dim": (_int, [_p]),
+    "cb_flatip_storage_dtype": (_int, [_p]),
+    "cb_flatip_reserve": (_int, [_p, _i64]),
+    "cb_flatip_add": (_int, [_p, _i64, _p]),
+    "cb_flatip_add_device": (_int, [_p, _i64, _p, _int, _p]),
+    "cb_flatip_reset": (_int, [_p]),
+    "cb_flatip_search": (_int, [_p, _i64, _p, _i64, _p, _p]),
+    "cb_flatip_search_device": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p]),
+    "cb_topk_merge_device": (_int, [_int, _i64, _i64, _p, _p, _i64, _i64, _p, _p, _p]),
+    "cb_flatip_get_rows": (_int, [_p, _i64, _i64, _p]),
+    "cb_flatip_device_rows": (_p, [_p]),
+    "cb_flatip_timing": (_int, [_p, _int]),
+    "cb_flatip_timing_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(_int)]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load the library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+                "(clipb200 has no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)   # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().cb_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != CB_OK:
+        raise NativeError(rc, last_error())
+
+
+def device_count() -> int:
+    n = _int(0)
+    rc = lib().cb_device_count(C.byref(n))
+    return n.value if rc == CB_OK else 0
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().cb_launch_count(1 if reset else 0))

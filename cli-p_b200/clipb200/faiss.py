@@ -1,0 +1,362 @@
+"""Drop-in for the subset of `import faiss` that CLI-P uses, backed by libclipb200.
+
+Reference call sites (under /root/reference):
+  faiss.IndexFlatIP(512)                                    build-index.py:80
+  faiss.IndexIVFFlat(quantizer, 512, 100, METRIC_INNER_PRODUCT)   build-index.py:81
+  index.train(x) / index.add(x)                             build-index.py:96,99,105,107
+  faiss.write_index(index, "images.index")                  build-index.py:109
+  faiss.read_index("images.index"); index.nprobe = 32       query-index.py:29-30,51
+  D, I = index.search(features, k + offset + 1)             query-index.py:111
+
+Semantics follow faiss's Python wrapper [UPSTREAM class_wrappers.py]: inputs are
+C-contiguous float32 numpy arrays of shape (n, d); search returns (D float32
+(nq,k), I int64 (nq,k)); shape/type problems raise AssertionError / TypeError;
+`k > 0`.  IndexIVFFlat is served by the same exact flat scan (a recall
+superset of IVF probing, as the north star demands): train() is accepted and
+ignored, nprobe is stored and validated only by the caller.
+
+Every search runs on the GPU through the C ABI.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+
+_MAGIC = b"CB2FLAT1"
+
+
+def _storage_code(storage) -> int:
+    if storage is None:
+        storage = os.environ.get("CLIPB200_STORAGE", "f32")
+    if storage in (N.CB_F32, N.CB_F16) and not isinstance(storage, str):
+        return int(storage)
+    s = str(storage).lower()
+    if s in ("f32", "fp32", "float32"):
+        return N.CB_F32
+    if s in ("f16", "fp16", "float16", "half"):
+        return N.CB_F16
+    raise ValueError(f"unknown storage dtype {storage!r}")
+
+
+def _as_f32_2d(x, d: int, what: str) -> np.ndarray:
+    x = np.ascontiguousarray(x)
+    if x.dtype != np.float32:
+        raise TypeError(f"{what}: expected float32, got {x.dtype}")
+    assert x.ndim == 2, f"{what}: expected a 2-D array, got shape {x.shape}"
+    assert x.shape[1] == d, f"{what}: dimension {x.shape[1]} != index dimension {d}"
+    return x
+
+
+class _Shard:
+    """One device-resident shard = one cb_index handle."""
+
+    def __init__(self, d: int, storage: int, device: int):
+        self.handle = C.c_void_p()
+        N.check(N.lib().cb_flatip_create(d, storage, device, C.byref(self.handle)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            N.lib().cb_flatip_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ntotal(self) -> int:
+        return int(N.lib().cb_flatip_ntotal(self.handle))
+
+
+class IndexFlatIP:
+    """Exact inner-product index; rows live in HBM, ids are add() order.
+
+    devices: CUDA ordinals holding the shards.  One device (default: the current
+    torch device if torch is imported and CUDA is initialised, else 0) gives the
+    plain single-GPU index.  Several devices shard every add() call contiguously
+    and merge per-device top-k on devices[0].
+    """
+
+    def __init__(self, d: int = 512, storage=None, devices: Optional[Sequence[int]] = None):
+        self.d = int(d)
+        self.metric_type = METRIC_INNER_PRODUCT
+        self.is_trained = True
+        self.verbose = False
+        self._storage = _storage_code(storage)
+        if devices is None:
+            env = os.environ.get("CLIPB200_DEVICES")
+            devices = [int(t) for t in env.split(",")] if env else [_default_device()]
+        self._devices = list(devices)
+        assert len(self._devices) >= 1
+        self._shards: List[_Shard] = [_Shard(self.d, self._storage, dev) for dev in self._devices]
+        # multi-device bookkeeping: per shard, segments (local_start, global_start, count)
+        self._segments: List[List[tuple]] = [[] for _ in self._devices]
+        self._ntotal = 0
+
+    # -- faiss attributes ------------------------------------------------------
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    @property
+    def storage(self) -> str:
+        return "f16" if self._storage == N.CB_F16 else "f32"
+
+    def train(self, x) -> None:  # flat indexes need no training
+        _as_f32_2d(x, self.d, "train")
+
+    def reset(self) -> None:
+        for sh in self._shards:
+            N.check(N.lib().cb_flatip_reset(sh.handle))
+        self._segments = [[] for _ in self._devices]
+        self._ntotal = 0
+
+    def reserve(self, n: int) -> None:
+        per = -(-int(n) // len(self._shards))
+        for sh in self._shards:
+            N.check(N.lib().cb_flatip_reserve(sh.handle, per))
+
+    # -- add -------------------------------------------------------------------
+    def add(self, x) -> None:
+        x = _as_f32_2d(x, self.d, "add")
+        n = x.shape[0]
+        if n == 0:
+            return
+        R = len(self._shards)
+        if R == 1:
+            N.check(N.lib().cb_flatip_add(self._shards[0].handle, n, x.ctypes.data_as(C.c_void_p)))
+        else:
+            per = -(-n // R)
+            for r, sh in enumerate(self._shards):
+                lo, hi = min(r * per, n), min((r + 1) * per, n)
+                if hi <= lo:
+                    continue
+                part = x[lo:hi]
+                local0 = sh.ntotal
+                N.check(N.lib().cb_flatip_add(sh.handle, hi - lo, part.ctypes.data_as(C.c_void_p)))
+                self._segments[r].append((local0, self._ntotal + lo, hi - lo))
+        self._ntotal += n
+
+    def add_device(self, x_dev, shard: int = 0) -> None:
+        """Append rows already on the GPU (torch CUDA tensor, fp16 or fp32, (n, d))."""
+        import torch
+        assert x_dev.is_cuda and x_dev.dim() == 2 and x_dev.shape[1] == self.d
+        assert x_dev.dtype in (torch.float16, torch.float32)
+        x_dev = x_dev.contiguous()
+        sh = self._shards[shard]
+        assert x_dev.device.index == sh.device
+        n = x_dev.shape[0]
+        src = N.CB_F16 if x_dev.dtype == torch.float16 else N.CB_F32
+        stream = torch.cuda.current_stream(x_dev.device).cuda_stream
+        local0 = sh.ntotal
+        N.check(N.lib().cb_flatip_add_device(sh.handle, n, C.c_void_p(x_dev.data_ptr()), src,
+                                             C.c_void_p(stream)))
+        if len(self._shards) > 1:
+            self._segments[shard].append((local0, self._ntotal, n))
+        self._ntotal += n
+
+    # -- search ----------------------------------------------------------------
+    def search(self, x, k: int):
+        x = _as_f32_2d(x, self.d, "search")
+        k = int(k)
+        assert k > 0, "search: k must be > 0"
+        nq = x.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        if nq == 0:
+            return D, I
+        if len(self._shards) == 1:
+            N.check(N.lib().cb_flatip_search(self._shards[0].handle, nq, x.ctypes.data_as(C.c_void_p), k,
+                                             D.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p)))
+            return D, I
+        import torch
+        q = torch.from_numpy(x)
+        Dt, It = self.search_device(q, k)
+        D[...] = Dt.cpu().numpy()
+        I[...] = It.cpu().numpy()
+        return D, I
+
+    def search_device(self, q, k: int):
+        """Device-resident search: q is a torch tensor (nq, d) float32 (host or any
+        device); returns torch CUDA tensors (D, I) on devices[0].  No host sync."""
+        import torch
+        k = int(k)
+        assert k > 0
+        nq = q.shape[0]
+        R = len(self._shards)
+        dev0 = torch.device("cuda", self._devices[0])
+        outs = []
+        for r, sh in enumerate(self._shards):
+            dev = torch.device("cuda", sh.device)
+            with torch.cuda.device(dev):
+                qd = q.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+                Dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+                Id = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                N.check(N.lib().cb_flatip_search_device(
+                    sh.handle, nq, C.c_void_p(qd.data_ptr()), k, C.c_void_p(Dd.data_ptr()),
+                    C.c_void_p(Id.data_ptr()), 0, C.c_void_p(stream)))
+                if R > 1:
+                    Id = self._local_to_global(r, Id)
+                outs.append((Dd, Id))
+        if R == 1:
+            return outs[0]
+        with torch.cuda.device(dev0):
+            Dall = torch.stack([d.to(dev0, non_blocking=True) for d, _ in outs])
+            Iall = torch.stack([i.to(dev0, non_blocking=True) for _, i in outs])
+            return merge_topk_device(Dall, Iall, k)
+
+    def _local_to_global(self, r: int, I_local):
+        import torch
+        segs = self._segments[r]
+        if not segs:
+            return I_local
+        dev = I_local.device
+        starts = torch.tensor([s[0] for s in segs], dtype=torch.int64, device=dev)
+        gstarts = torch.tensor([s[1] for s in segs], dtype=torch.int64, device=dev)
+        idx = torch.bucketize(I_local.clamp_min(0), starts, right=True) - 1
+        out = I_local - starts[idx] + gstarts[idx]
+        return torch.where(I_local < 0, I_local, out)
+
+    # -- reconstruct -------------------------------------------------------------
+    def reconstruct_n(self, n0: int = 0, ni: int = -1) -> np.ndarray:
+        if ni < 0:
+            ni = self._ntotal - n0
+        assert 0 <= n0 and n0 + ni <= self._ntotal
+        out = np.empty((ni, self.d), dtype=np.float32)
+        if len(self._shards) == 1:
+            N.check(N.lib().cb_flatip_get_rows(self._shards[0].handle, n0, ni, out.ctypes.data_as(C.c_void_p)))
+            return out
+        for r, sh in enumerate(self._shards):
+            for (l0, g0, cnt) in self._segments[r]:
+                lo, hi = max(g0, n0), min(g0 + cnt, n0 + ni)
+                if hi <= lo:
+                    continue
+                tmp = np.empty((hi - lo, self.d), dtype=np.float32)
+                N.check(N.lib().cb_flatip_get_rows(sh.handle, l0 + (lo - g0), hi - lo, tmp.ctypes.data_as(C.c_void_p)))
+                out[lo - n0:hi - n0] = tmp
+        return out
+
+    def reconstruct(self, i: int) -> np.ndarray:
+        return self.reconstruct_n(int(i), 1)[0]
+
+
+class IndexIVFFlat:
+    """Accepted for surface compatibility (build-index.py:81); searches exactly.
+
+    The north star replaces IVF probing by an exact flat scan, which returns a
+    superset-quality result (identical to IVF with nprobe == nlist).  `train` is a
+    no-op apart from argument validation; `nprobe` is kept as a plain attribute.
+    """
+
+    def __init__(self, quantizer: IndexFlatIP, d: int, nlist: int, metric: int = METRIC_INNER_PRODUCT):
+        assert isinstance(quantizer, IndexFlatIP), "quantizer must be an IndexFlatIP"
+        assert metric == METRIC_INNER_PRODUCT, "only METRIC_INNER_PRODUCT is supported"
+        assert int(d) == quantizer.d
+        self.quantizer = quantizer
+        self.d = int(d)
+        self.nlist = int(nlist)
+        self.nprobe = 1
+        self.metric_type = metric
+        self.is_trained = False
+        self._flat = quantizer   # the quantizer object doubles as the row store
+
+    @property
+    def ntotal(self) -> int:
+        return self._flat.ntotal
+
+    def train(self, x) -> None:
+        _as_f32_2d(x, self.d, "train")
+        self.is_trained = True
+
+    def add(self, x) -> None:
+        assert self.is_trained, "IndexIVFFlat.add before train (faiss raises here too)"
+        self._flat.add(x)
+
+    def search(self, x, k: int):
+        return self._flat.search(x, k)
+
+    def reset(self) -> None:
+        self._flat.reset()
+
+
+# ---- merge (the step after the cross-GPU gather) ---------------------------------
+
+def merge_topk_device(Dall, Iall, k: int, shard_stride_D: int = 0, shard_stride_I: int = 0,
+                      R: Optional[int] = None, nq: Optional[int] = None):
+    """Merge per-shard (R, nq, k) CUDA tensors into (nq, k) on the same device."""
+    import torch
+    if R is None:
+        R, nq = Dall.shape[0], Dall.shape[1]
+    dev = Dall.device
+    D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        N.check(N.lib().cb_topk_merge_device(R, nq, k, C.c_void_p(Dall.data_ptr()), C.c_void_p(Iall.data_ptr()),
+                                             shard_stride_D, shard_stride_I,
+                                             C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
+                                             C.c_void_p(stream)))
+    return D, I
+
+
+# ---- index file I/O ---------------------------------------------------------------
+# Own container (faiss's IwFl/IxFI interop is a "next" row):
+#   magic "CB2FLAT1" | u32 d | u32 storage | u64 ntotal | u32 kind (0 flat, 1 ivf shim) |
+#   u32 nlist | u32 nprobe | u32 reserved | rows float32 little-endian [ntotal, d]
+
+def write_index(index, path: str) -> None:
+    flat = index._flat if isinstance(index, IndexIVFFlat) else index
+    kind = 1 if isinstance(index, IndexIVFFlat) else 0
+    nlist = getattr(index, "nlist", 0)
+    nprobe = getattr(index, "nprobe", 0)
+    with open(path, "wb") as fh:
+        fh.write(_MAGIC)
+        fh.write(struct.pack("<IIQIIII", flat.d, flat._storage, flat.ntotal, kind, nlist, nprobe, 0))
+        step = 1 << 16
+        for lo in range(0, flat.ntotal, step):
+            rows = flat.reconstruct_n(lo, min(step, flat.ntotal - lo))
+            fh.write(rows.astype("<f4", copy=False).tobytes())
+
+
+def read_index(path: str, storage=None, devices: Optional[Sequence[int]] = None):
+    with open(path, "rb") as fh:
+        magic = fh.read(8)
+        if magic != _MAGIC:
+            raise RuntimeError(f"{path}: not a clipb200 index file (faiss-format interop is not implemented)")
+        d, st, ntotal, kind, nlist, nprobe, _ = struct.unpack("<IIQIIII", fh.read(32))
+        flat = IndexFlatIP(d, storage=st if storage is None else storage, devices=devices)
+        flat.reserve(ntotal)
+        step = 1 << 16
+        for lo in range(0, ntotal, step):
+            m = min(step, ntotal - lo)
+            buf = fh.read(m * d * 4)
+            if len(buf) != m * d * 4:
+                raise RuntimeError(f"{path}: truncated index file")
+            flat.add(np.frombuffer(buf, dtype="<f4").reshape(m, d).astype(np.float32, copy=False))
+    if kind == 1:
+        ivf = IndexIVFFlat(flat, d, nlist, METRIC_INNER_PRODUCT)
+        ivf.is_trained = True
+        ivf.nprobe = nprobe
+        return ivf
+    return flat
+
+
+def _default_device() -> int:
+    import sys
+    t = sys.modules.get("torch")
+    if t is not None and t.cuda.is_available() and t.cuda.is_initialized():
+        return int(t.cuda.current_device())
+    return int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("CLIPB200_USE_LOCAL_RANK") else 0

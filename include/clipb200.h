@@ -1,0 +1,111 @@
+/* clipb200 -- C ABI of the B200-native hot paths behind CLI-P's surface.
+ *
+ * The reference (ps-auxw/CLI-P) has no FFI of its own: its boundary is Python
+ * duck typing on two imported modules, `faiss` and `clip`.  Every entry point
+ * below names the reference call it replaces (file:line under /root/reference).
+ * Conventions (modelled on faiss's own c_api): int return code, 0 = OK,
+ * non-zero = error with a thread-local message from cb_last_error(); caller
+ * owns all in/out buffers; the library owns device-resident database shards and
+ * model weights; ids are int64 positions in add() order.  No function aborts,
+ * none has a CPU fallback: creating a handle without a CUDA device is an error.
+ *
+ * "_device" variants take device pointers and a cudaStream_t (passed as void*)
+ * and never synchronise; the plain variants take HOST pointers, do the
+ * host<->device copies themselves and return when the results are in host
+ * memory.
+ */
+#ifndef CLIPB200_H
+#define CLIPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_OK 0
+#define CB_ERR_INVALID 1   /* bad argument (shape, k <= 0, null pointer ...) */
+#define CB_ERR_CUDA 2      /* a CUDA runtime/driver call failed */
+#define CB_ERR_NOGPU 3     /* no CUDA device: there is no CPU fallback */
+#define CB_ERR_OOM 4
+#define CB_ERR_IO 5
+
+/* storage dtype of database rows / dtype of a device source buffer */
+#define CB_F32 0
+#define CB_F16 1
+
+typedef struct cb_index cb_index;
+
+/* ---- misc ------------------------------------------------------------- */
+const char *cb_last_error(void);
+int cb_abi_version(void);
+int cb_device_count(int *n);
+
+/* ---- exact inner-product index (replaces faiss.IndexFlatIP) ----------- */
+
+/* faiss.IndexFlatIP(512)                       build-index.py:80
+ * d must be 512 (CLIP ViT-B/32 embedding width); storage is CB_F16 (1024
+ * B/row, BASELINE configs 3-5) or CB_F32 (2048 B/row, what the reference
+ * stores).  The shard lives on CUDA device `device`. */
+int cb_flatip_create(int d, int storage_dtype, int device, cb_index **out);
+void cb_flatip_free(cb_index *ix);
+
+/* index.ntotal */
+int64_t cb_flatip_ntotal(const cb_index *ix);
+int cb_flatip_dim(const cb_index *ix);
+int cb_flatip_storage_dtype(const cb_index *ix);
+
+/* pre-size the shard (optional; add() grows geometrically otherwise) */
+int cb_flatip_reserve(cb_index *ix, int64_t n_rows);
+
+/* index.add(float32[n,512])                    build-index.py:99,107
+ * rows are appended; ids are implicit and sequential from ntotal. */
+int cb_flatip_add(cb_index *ix, int64_t n, const float *x_host);
+int cb_flatip_add_device(cb_index *ix, int64_t n, const void *x_dev, int src_dtype,
+                         void *stream);
+
+/* drop all rows, keep the allocation (index.reset()) */
+int cb_flatip_reset(cb_index *ix);
+
+/* D, I = index.search(float32[nq,512], k)      query-index.py:111
+ * D float32[nq,k] descending, I int64[nq,k]; unfilled slots I=-1,
+ * D=-3.4028235e38; equal scores: lower id first.  id_base is added to every
+ * returned id (the shard's first global row). */
+int cb_flatip_search(cb_index *ix, int64_t nq, const float *q_host, int64_t k,
+                     float *D_host, int64_t *I_host);
+int cb_flatip_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k,
+                            float *D_dev, int64_t *I_dev, int64_t id_base, void *stream);
+
+/* Merge R per-shard results into [nq][k] by (-score, id); ids < 0 are padding.
+ * Shard r's block [nq][k] starts at D_in + r*shard_stride_D (elements) and
+ * I_in + r*shard_stride_I; a stride <= 0 means densely packed [R][nq][k].  Runs
+ * on the current device.  This is the step after the single cross-GPU gather
+ * (SURVEY.md 8e), whose receive buffer holds each rank's D block and I block
+ * back to back. */
+int cb_topk_merge_device(int R, int64_t nq, int64_t k, const float *D_in,
+                         const int64_t *I_in, int64_t shard_stride_D, int64_t shard_stride_I,
+                         float *D_out, int64_t *I_out, void *stream);
+
+/* copy rows [start, start+n) back to the host as float32 (index.reconstruct_n;
+ * used by write_index, build-index.py:109) */
+int cb_flatip_get_rows(cb_index *ix, int64_t start, int64_t n, float *out_host);
+
+/* device pointer of the shard (rows are contiguous, ntotal x d of the storage
+ * dtype) -- for zero-copy ingest checks and benches */
+const void *cb_flatip_device_rows(const cb_index *ix);
+
+/* Live timing of the scan kernel (the dominant kernel of a search): when enabled,
+ * every scan launch is bracketed by CUDA events on its own stream (up to 256
+ * launches); timing_read waits for them, returns the summed duration and count
+ * and clears the list.  Used by bench.py for the roofline figure. */
+int cb_flatip_timing(cb_index *ix, int enable);
+int cb_flatip_timing_read(cb_index *ix, double *scan_ms_total, int *n_scans);
+
+/* kernel launches issued by this library on the calling thread since the last
+ * call with reset != 0 (bench.py's gpu_launches) */
+int64_t cb_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPB200_H */

@@ -1,0 +1,72 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/clipb200.h
+declares; the ctypes table mirrors the header; no compute is called."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "clipb200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from clipb200 import build
+    path = build.build()
+    return C.CDLL(path)
+
+
+def test_header_declares_something():
+    syms = declared_symbols()
+    assert "cb_flatip_search" in syms and "cb_last_error" in syms
+
+
+def test_every_declared_symbol_is_exported(lib):
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, f"declared in clipb200.h but not exported: {missing}"
+
+
+def test_ctypes_table_matches_header(lib):
+    from clipb200 import _native
+    assert sorted(_native.SIGNATURES) == declared_symbols()
+    assert _native.lib().cb_abi_version() >= 1
+
+
+def test_no_gpu_is_a_loud_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from clipb200 import _native, faiss
+    assert _native.device_count() == 0
+    with pytest.raises(_native.NativeError) as ei:
+        faiss.IndexFlatIP(512)
+    assert ei.value.code == _native.CB_ERR_NOGPU
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_bad_arguments_are_errors_not_crashes(lib):
+    from clipb200 import _native
+    L = _native.lib()
+    h = C.c_void_p()
+    assert L.cb_flatip_create(100, 0, 0, C.byref(h)) == _native.CB_ERR_INVALID
+    assert "512" in _native.last_error()
+    assert L.cb_flatip_create(512, 7, 0, C.byref(h)) == _native.CB_ERR_INVALID
+    assert L.cb_flatip_search(None, 1, None, 1, None, None) == _native.CB_ERR_INVALID
+
+
+def test_sass_is_sm100(lib):
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    from clipb200 import _native
+    out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
