@@ -48,6 +48,7 @@ SIGNATURES = {
     "cb_topk_merge_device": (_int, [_int, _i64, _i64, _p, _p, _i64, _i64, _p, _p, _p]),
     "cb_flatip_get_rows": (_int, [_p, _i64, _i64, _p]),
     "cb_flatip_device_rows": (_p, [_p]),
+    "cb_gemm_f16_device": (_int, [_int, _int, _int, _p, _p, _p, _p, _p, _p, _int, _int, _p]),
     "cb_flatip_timing": (_int, [_p, _int]),
     "cb_flatip_timing_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(_int)]),
 }

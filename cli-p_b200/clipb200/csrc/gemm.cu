@@ -1,0 +1,457 @@
+// Hand-written tcgen05 GEMM (sm_100a): TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (cta_group::1, kind::f16, M=128 x N=BN x K=16) -> fp32 accumulators in TMEM (double
+// buffered) -> tcgen05.ld epilogue fused with bias / QuickGELU / residual / pos-emb.
+//
+// Replaces the cuBLAS/cuDNN calls torch dispatches for openai/CLIP's conv1, in_proj,
+// out_proj, c_fc, c_proj, proj  (reference
+// call sites /root/reference/build-index.py:49, query-index.py:108).
+//
+// Persistent kernel, one CTA per SM, static tile schedule (n fastest so concurrently
+// running CTAs share A tiles through L2).  Warp roles (192 threads):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5  epilogue; warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows)
+#include "common.cuh"
+#include "gemm.cuh"
+
+#include <cuda.h>
+
+namespace cb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 fp16 = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 28;   // turns a protocol bug into a trap, not a hang
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
+    static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; both operands K-major
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t gets row (lane base + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, 128B swizzle: rows of 128 B, 8-row
+// atoms 1024 B apart (SBO); LBO is fixed (1) for swizzled K-major layouts; version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D fp32, A/B fp16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// ---- the kernel -------------------------------------------------------------------------
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs g, const int m_tiles, const int n_tiles) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t *empty = full + C::STAGES;
+    uint64_t *tfull = empty + C::STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < C::STAGES; i++) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1);
+            }
+            for (int i = 0; i < 2; i++) {
+                mbar_init(&tfull[i], 1);
+                mbar_init(&tempty[i], 4);      // one arrive per epilogue warp
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, C::TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+    const int num_tiles = m_tiles * n_tiles;
+    const int KB = g.K / BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < KB; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    uint8_t *sa = smem + stage * C::STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
+                    tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN, &full[stage]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < KB; kb++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t da = make_smem_desc(sa);
+                    const uint64_t db = make_smem_desc(sa + C::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        // advance 16 elements = 32 B along K inside the swizzle atom: +2 in 16-B units
+                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);          // frees the smem slot when the MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[as]);                 // accumulator complete -> epilogue
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;                          // TMEM lane quadrant this warp may touch
+        uint32_t as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const int row = m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < g.M;
+            int out_row = row;
+            const float *pos_row = nullptr;
+            if (EPI == EPI_PATCH) {
+                const int img = row / 49, p = row - img * 49;
+                out_row = row + img + 1;
+                pos_row = g.pos + (size_t)(1 + p) * g.N;
+            }
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, v);
+                const int n0 = n_blk * BN + c * 32;
+                float add[32];
+                if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) {
+                    if (g.bias) {
+                        const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + n0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 b = __ldg(b4 + j);
+                            add[4 * j] = b.x; add[4 * j + 1] = b.y; add[4 * j + 2] = b.z; add[4 * j + 3] = b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) add[j] = 0.f;
+                    }
+                } else if (EPI == EPI_PATCH) {
+                    const float4 *p4 = reinterpret_cast<const float4 *>(pos_row + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 b = row_ok ? __ldg(p4 + j) : make_float4(0, 0, 0, 0);
+                        add[4 * j] = b.x; add[4 * j + 1] = b.y; add[4 * j + 2] = b.z; add[4 * j + 3] = b.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) add[j] = 0.f;
+                }
+                uint4 rz[4];
+                if (EPI == EPI_BIAS_RESID) {
+                    const uint4 *r4 = reinterpret_cast<const uint4 *>(g.resid + (size_t)row * g.N + n0);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) rz[j] = row_ok ? r4[j] : make_uint4(0, 0, 0, 0);
+                }
+                tmem_ld_wait();
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) o[j] = __uint_as_float(v[j]) + add[j];
+                if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] = __fdividef(o[j], 1.0f + __expf(-1.702f * o[j]));
+                }
+                if (EPI == EPI_BIAS_RESID) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const __half2 *h = reinterpret_cast<const __half2 *>(&rz[j]);
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            float2 f = __half22float2(h[e]);
+                            o[8 * j + 2 * e] += f.x;
+                            o[8 * j + 2 * e + 1] += f.y;
+                        }
+                    }
+                }
+                if (row_ok) {
+                    if (EPI == EPI_F32) {
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.C) + (size_t)out_row * g.ldc + n0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    } else {
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(g.C) + (size_t)out_row * g.ldc + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            dst[j] = make_uint4(pack_h2(o[8 * j], o[8 * j + 1]), pack_h2(o[8 * j + 2], o[8 * j + 3]),
+                                                pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);     // accumulator stage drained
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp16 row-major [rows, cols] tensor, box = box_rows x 64 columns, 128B swizzle
+int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CB_ERR_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CB_ERR_CUDA; }
+    return CB_OK;
+}
+
+template <int BN, int EPI>
+int launch(const GemmArgs &g, cudaStream_t s) {
+    using C = Cfg<BN>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_done = true;
+    }
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, BN);
+    if (rc) return rc;
+    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = std::min(m_tiles * n_tiles, sms);
+    kern<<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, g, m_tiles, n_tiles);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+template <int BN>
+int dispatch_epi(const GemmArgs &g, cudaStream_t s) {
+    switch (g.epilogue) {
+        case EPI_BIAS: return launch<BN, EPI_BIAS>(g, s);
+        case EPI_BIAS_GELU: return launch<BN, EPI_BIAS_GELU>(g, s);
+        case EPI_BIAS_RESID: return launch<BN, EPI_BIAS_RESID>(g, s);
+        case EPI_PATCH: return launch<BN, EPI_PATCH>(g, s);
+        case EPI_F32: return launch<BN, EPI_F32>(g, s);
+    }
+    set_error("gemm_f16: unknown epilogue %d", g.epilogue);
+    return CB_ERR_INVALID;
+}
+
+// pick the N tile that wastes the fewest SM-rounds of the static persistent schedule
+int pick_bn(int M, int N, int sms) {
+    const int m_tiles = (M + BM - 1) / BM;
+    int best = 0;
+    double best_cost = 1e30;
+    for (int bn : {256, 192, 128}) {
+        if (N % bn) continue;
+        const int tiles = m_tiles * (N / bn);
+        const int rounds = (tiles + sms - 1) / sms;
+        // cost ~ rounds x tile width; narrow tiles pay more smem traffic per flop
+        double cost = (double)rounds * bn * (bn == 128 ? 1.08 : 1.0);
+        if (cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+}  // namespace
+
+int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
+    CB_REQUIRE(g.A && g.W && g.C, "gemm_f16: null operand");
+    CB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm_f16: empty shape");
+    CB_REQUIRE(g.K % BK == 0, "gemm_f16: K=%d must be a multiple of %d", g.K, BK);
+    CB_REQUIRE(g.N % 128 == 0, "gemm_f16: N=%d must be a multiple of 128", g.N);
+    CB_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0,
+               "gemm_f16: operands must be 16-byte aligned");
+    CB_REQUIRE(g.epilogue != EPI_BIAS_RESID || g.resid, "gemm_f16: residual epilogue without residual");
+    CB_REQUIRE(g.epilogue != EPI_PATCH || g.pos, "gemm_f16: patch epilogue without pos-emb");
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int bn = pick_bn(g.M, g.N, sms);
+    if (const char *e = getenv("CLIPB200_GEMM_BN")) {
+        int v = atoi(e);
+        if ((v == 128 || v == 192 || v == 256) && g.N % v == 0) bn = v;
+    }
+    switch (bn) {
+        case 256: return dispatch_epi<256>(g, stream);
+        case 192: return dispatch_epi<192>(g, stream);
+        case 128: return dispatch_epi<128>(g, stream);
+    }
+    set_error("gemm_f16: no tile shape for N=%d", g.N);
+    return CB_ERR_INVALID;
+}
+
+}  // namespace cb
+
+extern "C" int cb_gemm_f16_device(int M, int N, int K, const void *A, const void *W, const float *bias,
+                                  const void *resid, const float *pos, void *C, int ldc, int epilogue,
+                                  void *stream) {
+    cb::GemmArgs g;
+    g.A = (const __half *)A; g.W = (const __half *)W; g.bias = bias; g.resid = (const __half *)resid;
+    g.pos = pos; g.C = C; g.M = M; g.N = N; g.K = K; g.ldc = ldc > 0 ? ldc : N; g.epilogue = epilogue;
+    return cb::gemm_f16(g, (cudaStream_t)stream);
+}

@@ -1,0 +1,34 @@
+// tcgen05 / TMEM / TMA GEMM for the CLIP towers (sm_100a).
+//   C[M,N] = epilogue( A[M,K] (fp16, row-major) x W[N,K]^T (fp16, row-major = torch Linear weight) )
+// fp32 accumulation in tensor memory; fused epilogues.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cb {
+
+enum GemmEpilogue : int {
+    EPI_BIAS = 0,        // C = acc + bias                      (in_proj)
+    EPI_BIAS_GELU = 1,   // C = quickgelu(acc + bias)           (c_fc)      x*sigmoid(1.702x)
+    EPI_BIAS_RESID = 2,  // C = resid + acc + bias              (out_proj, c_proj); C may alias resid
+    EPI_PATCH = 3,       // C[row + row/49 + 1] = acc + pos[1 + row%49]   (conv1 as GEMM + pos-emb)
+    EPI_F32 = 4,         // Cf32 = acc                          (visual.proj / text_projection)
+};
+
+struct GemmArgs {
+    const __half *A;     // [M,K]
+    const __half *W;     // [N,K]
+    const float *bias;   // [N] fp32 (EPI_BIAS*, may be null = 0)
+    const __half *resid; // [M,N] (EPI_BIAS_RESID)
+    const float *pos;    // [50,N] fp32 (EPI_PATCH)
+    void *C;             // fp16 [M,N] (row stride ldc) or fp32 for EPI_F32
+    int M, N, K;
+    int ldc;             // elements
+    int epilogue;
+};
+
+// returns a CB_* code; launches on `stream`
+int gemm_f16(const GemmArgs &g, cudaStream_t stream);
+
+}  // namespace cb

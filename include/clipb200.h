@@ -101,6 +101,18 @@ const void *cb_flatip_device_rows(const cb_index *ix);
 int cb_flatip_timing(cb_index *ix, int enable);
 int cb_flatip_timing_read(cb_index *ix, double *scan_ms_total, int *n_scans);
 
+/* ---- tcgen05 GEMM building block (exported for unit tests and benches) ----
+ * C[M,N] = epilogue(A[M,K] fp16 row-major x W[N,K]^T fp16 row-major), fp32
+ * accumulation in tensor memory.  Replaces the cuBLAS calls torch dispatches for
+ * openai/CLIP's nn.Linear / conv1 / `@ proj` inside model.encode_image /
+ * encode_text (build-index.py:49, query-index.py:108).  epilogue: 0 bias,
+ * 1 bias+QuickGELU, 2 bias+residual (C may alias resid), 3 patch-embed scatter
+ * + pos-emb, 4 plain fp32 output.  K % 64 == 0, N % 128 == 0; all device
+ * pointers, 16-byte aligned; ldc in elements (0 = N). */
+int cb_gemm_f16_device(int M, int N, int K, const void *A, const void *W, const float *bias,
+                       const void *resid, const float *pos, void *C, int ldc, int epilogue,
+                       void *stream);
+
 /* kernel launches issued by this library on the calling thread since the last
  * call with reset != 0 (bench.py's gpu_launches) */
 int64_t cb_launch_count(int reset);

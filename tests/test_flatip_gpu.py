@@ -174,9 +174,10 @@ def test_merge_kernel_matches_oracle(faiss):
     Ds[2, :, 60:] = F.NEG_FLT_MAX
     Is[2, :, 60:] = -1                      # a short shard
     Ds[5, 1, :] = Ds[4, 1, :]               # cross-shard exact ties
-    for kk in (100, 37):
-        D, I = faiss.merge_topk_device(torch.from_numpy(Ds).cuda(), torch.from_numpy(Is).cuda(), kk)
-        Dref, Iref = F.merge_topk(Ds, Is, kk)
+    for kk in (100, 37):      # per-shard lists and the merged list have the same length k
+        Dk, Ik = Ds[:, :, :kk].copy(), Is[:, :, :kk].copy()
+        D, I = faiss.merge_topk_device(torch.from_numpy(Dk).cuda(), torch.from_numpy(Ik).cuda(), kk)
+        Dref, Iref = F.merge_topk(Dk, Ik, kk)
         assert (I.cpu().numpy() == Iref).all() and (D.cpu().numpy() == Dref).all()
     # very large R*k goes through the global-memory sort
     R, nq, k = 8, 2, 2000
