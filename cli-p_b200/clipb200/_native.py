@@ -48,6 +48,22 @@ SIGNATURES = {
     "cb_topk_merge_device": (_int, [_int, _i64, _i64, _p, _p, _i64, _i64, _p, _p, _p]),
     "cb_flatip_get_rows": (_int, [_p, _i64, _i64, _p]),
     "cb_flatip_device_rows": (_p, [_p]),
+    "cb_clip_create": (_int, [_int, _int, _int, C.POINTER(_p)]),
+    "cb_clip_set_param": (_int, [_p, C.c_char_p, _p, _i64]),
+    "cb_clip_finalize": (_int, [_p]),
+    "cb_clip_free": (None, [_p]),
+    "cb_clip_encode_image_u8_device": (_int, [_p, _i64, _p, _p, _int, _p]),
+    "cb_clip_encode_image_f32_device": (_int, [_p, _i64, _p, _p, _int, _p]),
+    "cb_clip_encode_image_u8": (_int, [_p, _i64, _p, _p, _int]),
+    "cb_clip_encode_text_device": (_int, [_p, _i64, _p, _p, _int, _p]),
+    "cb_clip_encode_text": (_int, [_p, _i64, _p, _p, _int]),
+    "cb_clip_timing": (_int, [_p, _int]),
+    "cb_clip_timing_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_int)]),
+    "cb_layernorm_f16_device": (_int, [_p, _p, _p, _p, _int, _int, _int, _p, _p, _int, _p]),
+    "cb_attention_f16_device": (_int, [_p, _p, _int, _int, _int, _int, _p]),
+    "cb_preprocess_u8_device": (_int, [_p, _p, _int, _p]),
+    "cb_preprocess_f32_device": (_int, [_p, _p, _int, _p]),
+    "cb_l2norm_f32_device": (_int, [_p, _p, _int, _int, _p]),
     "cb_gemm_f16_device": (_int, [_int, _int, _int, _p, _p, _p, _p, _p, _p, _int, _int, _p]),
     "cb_flatip_timing": (_int, [_p, _int]),
     "cb_flatip_timing_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(_int)]),

@@ -1,0 +1,465 @@
+// CLIP ViT-B/32 towers on the tcgen05 GEMM + helper kernels: model handle, parameter
+// loading by openai/CLIP state-dict name, encode_image / encode_text.
+//
+// Replaces `model.encode_image(image)` (/root/reference/build-index.py:49, with the
+// L2 normalisation of :50 fused at the end) and `model.encode_text(texts)`
+// (/root/reference/query-index.py:108).  Activations are fp16 with fp32 accumulation and
+// fp32 LayerNorm statistics -- the precision the reference's own GPU path runs at
+// (clip.load converts weights to fp16 on CUDA devices).
+//
+// HBM layout (B images, rows = B*50, W = 768):
+//   patches [B*49, 3072] fp16   im2col, column = py*96 + px*3 + c (conv1 weight permuted to match)
+//   x       [rows, W]    fp16   residual stream (token-major per image: class token first)
+//   h       [rows, W]    fp16   LayerNorm output = GEMM A operand
+//   qkv     [rows, 3W]   fp16   q | k | v, heads of 64 columns
+//   att     [rows, W]    fp16
+//   mlp     [rows, 4W]   fp16
+//   cls     [B, W] fp16 -> emb [B, 512] fp32 -> out (L2-normalised)
+// The text tower reuses the same buffers with rows = B*77, W = 512.
+#include "common.cuh"
+#include "gemm.cuh"
+#include "vit_kernels.cuh"
+
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace cb;
+
+namespace {
+
+struct Param {
+    void *dev = nullptr;
+    int64_t numel = 0;
+    bool half = false;
+};
+
+struct LayerW {
+    const __half *w_qkv, *w_o, *w_fc, *w_proj;
+    const float *b_qkv, *b_o, *b_fc, *b_proj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+constexpr int VW = 768, VL = 50, VH = 12, TW = 512, TL = 77, TH = 8, LAYERS = 12, ED = 512, VOCAB = 49408;
+
+}  // namespace
+
+struct cb_clip {
+    int device = 0;
+    int max_img = 0, max_txt = 0;
+    std::map<std::string, Param> params;
+    bool finalized = false;
+    LayerW vis[LAYERS], txt[LAYERS];
+    const __half *conv1_w = nullptr, *vproj_w = nullptr, *tproj_w = nullptr;
+    const float *vpos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
+    const float *tok_emb = nullptr, *tpos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+    float *cls_pos = nullptr;     // class_embedding + positional_embedding[0]
+    // workspace
+    __half *patches = nullptr, *x = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr;
+    float *emb = nullptr;
+    int *eot = nullptr;
+    // staging for the host-pointer entry points
+    uint8_t *d_img = nullptr;
+    int32_t *d_ids = nullptr;
+    float *d_out = nullptr;
+    cudaStream_t stream = nullptr;
+    // live GEMM timing (bench.py roofline)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    int ev_n = 0;
+    double gemm_flops = 0;
+};
+
+namespace {
+
+int upload(cb_clip *m, const std::string &name, const float *host, int64_t numel, bool as_half) {
+    Param &p = m->params[name];
+    if (p.dev) { cudaFree(p.dev); p.dev = nullptr; }
+    p.numel = numel;
+    p.half = as_half;
+    if (as_half) {
+        std::vector<__half> tmp((size_t)numel);
+        for (int64_t i = 0; i < numel; i++) tmp[i] = __float2half_rn(host[i]);
+        CB_CUDA(cudaMalloc(&p.dev, (size_t)numel * 2));
+        CB_CUDA(cudaMemcpy(p.dev, tmp.data(), (size_t)numel * 2, cudaMemcpyHostToDevice));
+    } else {
+        CB_CUDA(cudaMalloc(&p.dev, (size_t)std::max<int64_t>(numel, 1) * 4));
+        CB_CUDA(cudaMemcpy(p.dev, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+    }
+    return CB_OK;
+}
+
+bool ends_with(const std::string &s, const char *suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+template <typename T>
+int need(cb_clip *m, const std::string &name, int64_t numel, bool half, const T **out) {
+    auto it = m->params.find(name);
+    if (it == m->params.end()) { set_error("cb_clip_finalize: parameter %s was never set", name.c_str()); return CB_ERR_INVALID; }
+    if (it->second.numel != numel || it->second.half != half) {
+        set_error("cb_clip_finalize: parameter %s has %lld elements, expected %lld", name.c_str(),
+                  (long long)it->second.numel, (long long)numel);
+        return CB_ERR_INVALID;
+    }
+    *out = reinterpret_cast<const T *>(it->second.dev);
+    return CB_OK;
+}
+
+int bind_blocks(cb_clip *m, const char *prefix, int W, LayerW *lw) {
+    for (int i = 0; i < LAYERS; i++) {
+        const std::string b = std::string(prefix) + ".resblocks." + std::to_string(i) + ".";
+        int rc = 0;
+        rc |= need(m, b + "attn.in_proj_weight", 3ll * W * W, true, &lw[i].w_qkv);
+        rc |= need(m, b + "attn.out_proj.weight", 1ll * W * W, true, &lw[i].w_o);
+        rc |= need(m, b + "mlp.c_fc.weight", 4ll * W * W, true, &lw[i].w_fc);
+        rc |= need(m, b + "mlp.c_proj.weight", 4ll * W * W, true, &lw[i].w_proj);
+        rc |= need(m, b + "attn.in_proj_bias", 3ll * W, false, &lw[i].b_qkv);
+        rc |= need(m, b + "attn.out_proj.bias", 1ll * W, false, &lw[i].b_o);
+        rc |= need(m, b + "mlp.c_fc.bias", 4ll * W, false, &lw[i].b_fc);
+        rc |= need(m, b + "mlp.c_proj.bias", 1ll * W, false, &lw[i].b_proj);
+        rc |= need(m, b + "ln_1.weight", W, false, &lw[i].ln1_g);
+        rc |= need(m, b + "ln_1.bias", W, false, &lw[i].ln1_b);
+        rc |= need(m, b + "ln_2.weight", W, false, &lw[i].ln2_g);
+        rc |= need(m, b + "ln_2.bias", W, false, &lw[i].ln2_b);
+        if (rc) return CB_ERR_INVALID;
+    }
+    return CB_OK;
+}
+
+int timed_gemm(cb_clip *m, const GemmArgs &g, cudaStream_t s) {
+    const bool t = m->timing && m->ev_n + 2 <= (int)m->ev.size();
+    if (t) CB_CUDA(cudaEventRecord(m->ev[m->ev_n], s));
+    int rc = gemm_f16(g, s);
+    if (rc) return rc;
+    if (t) {
+        CB_CUDA(cudaEventRecord(m->ev[m->ev_n + 1], s));
+        m->ev_n += 2;
+        m->gemm_flops += 2.0 * g.M * g.N * g.K;
+    }
+    return CB_OK;
+}
+
+GemmArgs mk(const __half *A, const __half *W, const float *bias, const __half *resid, void *C, int M, int N, int K, int epi) {
+    GemmArgs g;
+    g.A = A; g.W = W; g.bias = bias; g.resid = resid; g.pos = nullptr; g.C = C;
+    g.M = M; g.N = N; g.K = K; g.ldc = N; g.epilogue = epi;
+    return g;
+}
+
+// 12 residual attention blocks over x [B*L, W] (in place)
+int run_blocks(cb_clip *m, const LayerW *lw, int W, int heads, int B, int L, bool causal, cudaStream_t s) {
+    const int rows = B * L;
+    for (int i = 0; i < LAYERS; i++) {
+        int rc;
+        if ((rc = layernorm_f16(m->x, m->h, lw[i].ln1_g, lw[i].ln1_b, rows, W, 1, nullptr, nullptr, 0, s))) return rc;
+        if ((rc = timed_gemm(m, mk(m->h, lw[i].w_qkv, lw[i].b_qkv, nullptr, m->qkv, rows, 3 * W, W, EPI_BIAS), s))) return rc;
+        if ((rc = attention_f16(m->qkv, m->att, B, L, heads, causal, s))) return rc;
+        if ((rc = timed_gemm(m, mk(m->att, lw[i].w_o, lw[i].b_o, m->x, m->x, rows, W, W, EPI_BIAS_RESID), s))) return rc;
+        if ((rc = layernorm_f16(m->x, m->h, lw[i].ln2_g, lw[i].ln2_b, rows, W, 1, nullptr, nullptr, 0, s))) return rc;
+        if ((rc = timed_gemm(m, mk(m->h, lw[i].w_fc, lw[i].b_fc, nullptr, m->mlp, rows, 4 * W, W, EPI_BIAS_GELU), s))) return rc;
+        if ((rc = timed_gemm(m, mk(m->mlp, lw[i].w_proj, lw[i].b_proj, m->x, m->x, rows, W, 4 * W, EPI_BIAS_RESID), s))) return rc;
+    }
+    return CB_OK;
+}
+
+// patches (already in m->patches) -> out [B,512] fp32
+int vision_from_patches(cb_clip *m, int B, float *out_dev, int normalize, cudaStream_t s) {
+    int rc;
+    GemmArgs g = mk(m->patches, m->conv1_w, nullptr, nullptr, m->x, B * 49, VW, 3072, EPI_PATCH);
+    g.pos = m->vpos;
+    if ((rc = timed_gemm(m, g, s))) return rc;
+    // ln_pre in place; class-token rows (row % 50 == 0) come from class_embedding + pos[0]
+    if ((rc = layernorm_f16(m->x, m->x, m->ln_pre_g, m->ln_pre_b, B * VL, VW, 1, nullptr, m->cls_pos, VL, s))) return rc;
+    if ((rc = run_blocks(m, m->vis, VW, VH, B, VL, false, s))) return rc;
+    if ((rc = layernorm_f16(m->x, m->cls, m->ln_post_g, m->ln_post_b, B, VW, VL, nullptr, nullptr, 0, s))) return rc;
+    float *emb = normalize ? m->emb : out_dev;
+    if ((rc = timed_gemm(m, mk(m->cls, m->vproj_w, nullptr, nullptr, emb, B, ED, VW, EPI_F32), s))) return rc;
+    if (normalize && (rc = l2norm_rows_f32(emb, out_dev, B, ED, s))) return rc;
+    return CB_OK;
+}
+
+int text_forward(cb_clip *m, int B, const int32_t *ids_dev, float *out_dev, int normalize, cudaStream_t s) {
+    int rc;
+    if ((rc = text_embed(ids_dev, m->tok_emb, m->tpos, m->x, m->eot, B, TL, TW, VOCAB, s))) return rc;
+    if ((rc = run_blocks(m, m->txt, TW, TH, B, TL, true, s))) return rc;
+    // ln_final only on the EOT rows (LayerNorm is per-row, so gathering first is exact)
+    if ((rc = layernorm_f16(m->x, m->cls, m->lnf_g, m->lnf_b, B, TW, 1, m->eot, nullptr, 0, s))) return rc;
+    float *emb = normalize ? m->emb : out_dev;
+    if ((rc = timed_gemm(m, mk(m->cls, m->tproj_w, nullptr, nullptr, emb, B, ED, TW, EPI_F32), s))) return rc;
+    if (normalize && (rc = l2norm_rows_f32(emb, out_dev, B, ED, s))) return rc;
+    return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_clip_create(int device, int max_image_batch, int max_text_batch, cb_clip **out) {
+    CB_REQUIRE(out != nullptr, "cb_clip_create: out is null");
+    *out = nullptr;
+    CB_REQUIRE(max_image_batch >= 0 && max_text_batch >= 0 && max_image_batch + max_text_batch > 0,
+               "cb_clip_create: batch capacities must be >= 0 and not both 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("cb_clip_create: no CUDA device (this library has no CPU fallback)");
+        return CB_ERR_NOGPU;
+    }
+    CB_REQUIRE(device >= 0 && device < ndev, "cb_clip_create: device %d out of range", device);
+    DeviceGuard g(device);
+    cb_clip *m = new (std::nothrow) cb_clip();
+    if (!m) { set_error("out of host memory"); return CB_ERR_OOM; }
+    m->device = device;
+    m->max_img = max_image_batch;
+    m->max_txt = max_text_batch;
+    // workspace: the larger of the two towers, element counts
+    const size_t rows_v = (size_t)max_image_batch * VL, rows_t = (size_t)max_text_batch * TL;
+    const size_t n_x = std::max(rows_v * VW, rows_t * TW);
+    const size_t n_qkv = 3 * n_x, n_mlp = 4 * n_x;
+    const size_t n_cls = std::max((size_t)max_image_batch * VW, (size_t)max_text_batch * TW);
+    const size_t nb = std::max(max_image_batch, max_text_batch);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 256)); };
+    A((void **)&m->patches, (size_t)max_image_batch * 49 * 3072 * 2);
+    A((void **)&m->x, n_x * 2); A((void **)&m->h, n_x * 2); A((void **)&m->att, n_x * 2);
+    A((void **)&m->qkv, n_qkv * 2); A((void **)&m->mlp, n_mlp * 2);
+    A((void **)&m->cls, n_cls * 2); A((void **)&m->emb, nb * ED * 4); A((void **)&m->eot, nb * 4);
+    A((void **)&m->d_img, (size_t)max_image_batch * 224 * 224 * 3);
+    A((void **)&m->d_ids, (size_t)max_text_batch * TL * 4);
+    A((void **)&m->d_out, nb * ED * 4);
+    A((void **)&m->cls_pos, VW * 4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cb_clip_create: %s", cudaGetErrorString(e));
+        cb_clip_free(m);
+        return e == cudaErrorMemoryAllocation ? CB_ERR_OOM : CB_ERR_CUDA;
+    }
+    *out = m;
+    return CB_OK;
+}
+
+void cb_clip_free(cb_clip *m) {
+    if (!m) return;
+    DeviceGuard g(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (auto &kv : m->params) cudaFree(kv.second.dev);
+    void *bufs[] = {m->patches, m->x, m->h, m->qkv, m->att, m->mlp, m->cls, m->emb, m->eot, m->d_img, m->d_ids, m->d_out, m->cls_pos};
+    for (void *p : bufs) cudaFree(p);
+    for (cudaEvent_t ev : m->ev) cudaEventDestroy(ev);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int cb_clip_set_param(cb_clip *m, const char *name_c, const float *host, int64_t numel) {
+    CB_REQUIRE(m && name_c && host, "cb_clip_set_param: null argument");
+    CB_REQUIRE(numel >= 0, "cb_clip_set_param: numel < 0");
+    DeviceGuard g(m->device);
+    const std::string name(name_c);
+    m->finalized = false;
+    if (name == "visual.conv1.weight") {
+        // [768][c][py][px] -> [768][py][px][c] so a patch row is 96 contiguous values
+        CB_REQUIRE(numel == 768ll * 3072, "visual.conv1.weight: expected 768*3*32*32 elements");
+        std::vector<float> t((size_t)numel);
+        for (int o = 0; o < 768; o++)
+            for (int c = 0; c < 3; c++)
+                for (int p = 0; p < 1024; p++) t[(size_t)o * 3072 + p * 3 + c] = host[(size_t)o * 3072 + c * 1024 + p];
+        return upload(m, name, t.data(), numel, true);
+    }
+    if (name == "visual.proj" || name == "text_projection") {
+        // stored [in, 512] and applied as x @ P: the GEMM wants [512, in] (K-major)
+        CB_REQUIRE(numel % ED == 0, "%s: element count not a multiple of 512", name_c);
+        const int64_t in = numel / ED;
+        std::vector<float> t((size_t)numel);
+        for (int64_t i = 0; i < in; i++)
+            for (int64_t o = 0; o < ED; o++) t[(size_t)o * in + i] = host[(size_t)i * ED + o];
+        return upload(m, name, t.data(), numel, true);
+    }
+    const bool gemm_w = ends_with(name, "in_proj_weight") || ends_with(name, "out_proj.weight") ||
+                        ends_with(name, "c_fc.weight") || ends_with(name, "c_proj.weight");
+    return upload(m, name, host, numel, gemm_w);
+}
+
+int cb_clip_finalize(cb_clip *m) {
+    CB_REQUIRE(m != nullptr, "cb_clip_finalize: null handle");
+    DeviceGuard g(m->device);
+    int rc = 0;
+    const float *cls_emb = nullptr;
+    rc |= need(m, "visual.conv1.weight", 768ll * 3072, true, &m->conv1_w);
+    rc |= need(m, "visual.class_embedding", VW, false, &cls_emb);
+    rc |= need(m, "visual.positional_embedding", 1ll * VL * VW, false, &m->vpos);
+    rc |= need(m, "visual.ln_pre.weight", VW, false, &m->ln_pre_g);
+    rc |= need(m, "visual.ln_pre.bias", VW, false, &m->ln_pre_b);
+    rc |= need(m, "visual.ln_post.weight", VW, false, &m->ln_post_g);
+    rc |= need(m, "visual.ln_post.bias", VW, false, &m->ln_post_b);
+    rc |= need(m, "visual.proj", 1ll * VW * ED, true, &m->vproj_w);
+    rc |= need(m, "token_embedding.weight", 1ll * VOCAB * TW, false, &m->tok_emb);
+    rc |= need(m, "positional_embedding", 1ll * TL * TW, false, &m->tpos);
+    rc |= need(m, "ln_final.weight", TW, false, &m->lnf_g);
+    rc |= need(m, "ln_final.bias", TW, false, &m->lnf_b);
+    rc |= need(m, "text_projection", 1ll * TW * ED, true, &m->tproj_w);
+    if (rc) return CB_ERR_INVALID;
+    if ((rc = bind_blocks(m, "visual.transformer", VW, m->vis))) return rc;
+    if ((rc = bind_blocks(m, "transformer", TW, m->txt))) return rc;
+    // class token row before ln_pre = class_embedding + positional_embedding[0]
+    std::vector<float> a(VW), b(VW);
+    CB_CUDA(cudaMemcpy(a.data(), cls_emb, VW * 4, cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(b.data(), m->vpos, VW * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < VW; i++) a[i] += b[i];
+    CB_CUDA(cudaMemcpy(m->cls_pos, a.data(), VW * 4, cudaMemcpyHostToDevice));
+    m->finalized = true;
+    return CB_OK;
+}
+
+#define CLIP_READY(m, fn)                                                              \
+    CB_REQUIRE((m) != nullptr, fn ": null handle");                                     \
+    CB_REQUIRE((m)->finalized, fn ": parameters not finalized (call cb_clip_finalize)")
+
+int cb_clip_encode_image_u8_device(cb_clip *m, int64_t B, const uint8_t *hwc_dev, float *out_dev, int normalize,
+                                   void *stream) {
+    CLIP_READY(m, "cb_clip_encode_image_u8_device");
+    CB_REQUIRE(B >= 0, "cb_clip_encode_image_u8_device: B < 0");
+    if (B == 0) return CB_OK;
+    CB_REQUIRE(hwc_dev && out_dev, "cb_clip_encode_image_u8_device: null buffer");
+    CB_REQUIRE(m->max_img > 0, "cb_clip_encode_image_u8_device: handle created with max_image_batch = 0");
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t lo = 0; lo < B; lo += m->max_img) {
+        const int b = (int)std::min<int64_t>(m->max_img, B - lo);
+        int rc = preprocess_u8(hwc_dev + (size_t)lo * 224 * 224 * 3, m->patches, b, s);
+        if (rc) return rc;
+        if ((rc = vision_from_patches(m, b, out_dev + lo * ED, normalize, s))) return rc;
+    }
+    return CB_OK;
+}
+
+int cb_clip_encode_image_f32_device(cb_clip *m, int64_t B, const float *nchw_dev, float *out_dev, int normalize,
+                                    void *stream) {
+    CLIP_READY(m, "cb_clip_encode_image_f32_device");
+    CB_REQUIRE(B >= 0, "cb_clip_encode_image_f32_device: B < 0");
+    if (B == 0) return CB_OK;
+    CB_REQUIRE(nchw_dev && out_dev, "cb_clip_encode_image_f32_device: null buffer");
+    CB_REQUIRE(m->max_img > 0, "cb_clip_encode_image_f32_device: handle created with max_image_batch = 0");
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t lo = 0; lo < B; lo += m->max_img) {
+        const int b = (int)std::min<int64_t>(m->max_img, B - lo);
+        int rc = preprocess_f32(nchw_dev + (size_t)lo * 3 * 224 * 224, m->patches, b, s);
+        if (rc) return rc;
+        if ((rc = vision_from_patches(m, b, out_dev + lo * ED, normalize, s))) return rc;
+    }
+    return CB_OK;
+}
+
+int cb_clip_encode_text_device(cb_clip *m, int64_t B, const int32_t *ids_dev, float *out_dev, int normalize,
+                               void *stream) {
+    CLIP_READY(m, "cb_clip_encode_text_device");
+    CB_REQUIRE(B >= 0, "cb_clip_encode_text_device: B < 0");
+    if (B == 0) return CB_OK;
+    CB_REQUIRE(ids_dev && out_dev, "cb_clip_encode_text_device: null buffer");
+    CB_REQUIRE(m->max_txt > 0, "cb_clip_encode_text_device: handle created with max_text_batch = 0");
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t lo = 0; lo < B; lo += m->max_txt) {
+        const int b = (int)std::min<int64_t>(m->max_txt, B - lo);
+        int rc = text_forward(m, b, ids_dev + lo * TL, out_dev + lo * ED, normalize, s);
+        if (rc) return rc;
+    }
+    return CB_OK;
+}
+
+int cb_clip_encode_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host, int normalize) {
+    CLIP_READY(m, "cb_clip_encode_image_u8");
+    CB_REQUIRE(B >= 0, "cb_clip_encode_image_u8: B < 0");
+    if (B == 0) return CB_OK;
+    CB_REQUIRE(hwc_host && out_host, "cb_clip_encode_image_u8: null buffer");
+    CB_REQUIRE(m->max_img > 0, "cb_clip_encode_image_u8: handle created with max_image_batch = 0");
+    DeviceGuard g(m->device);
+    const size_t img_bytes = 224 * 224 * 3;
+    for (int64_t lo = 0; lo < B; lo += m->max_img) {
+        const int b = (int)std::min<int64_t>(m->max_img, B - lo);
+        CB_CUDA(cudaMemcpyAsync(m->d_img, hwc_host + (size_t)lo * img_bytes, (size_t)b * img_bytes,
+                                cudaMemcpyHostToDevice, m->stream));
+        int rc = cb_clip_encode_image_u8_device(m, b, m->d_img, m->d_out, normalize, m->stream);
+        if (rc) return rc;
+        CB_CUDA(cudaMemcpyAsync(out_host + lo * ED, m->d_out, (size_t)b * ED * 4, cudaMemcpyDeviceToHost, m->stream));
+        CB_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return CB_OK;
+}
+
+int cb_clip_encode_text(cb_clip *m, int64_t B, const int32_t *ids_host, float *out_host, int normalize) {
+    CLIP_READY(m, "cb_clip_encode_text");
+    CB_REQUIRE(B >= 0, "cb_clip_encode_text: B < 0");
+    if (B == 0) return CB_OK;
+    CB_REQUIRE(ids_host && out_host, "cb_clip_encode_text: null buffer");
+    CB_REQUIRE(m->max_txt > 0, "cb_clip_encode_text: handle created with max_text_batch = 0");
+    DeviceGuard g(m->device);
+    for (int64_t lo = 0; lo < B; lo += m->max_txt) {
+        const int b = (int)std::min<int64_t>(m->max_txt, B - lo);
+        CB_CUDA(cudaMemcpyAsync(m->d_ids, ids_host + lo * TL, (size_t)b * TL * 4, cudaMemcpyHostToDevice, m->stream));
+        int rc = cb_clip_encode_text_device(m, b, m->d_ids, m->d_out, normalize, m->stream);
+        if (rc) return rc;
+        CB_CUDA(cudaMemcpyAsync(out_host + lo * ED, m->d_out, (size_t)b * ED * 4, cudaMemcpyDeviceToHost, m->stream));
+        CB_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return CB_OK;
+}
+
+int cb_clip_timing(cb_clip *m, int enable) {
+    CB_REQUIRE(m != nullptr, "cb_clip_timing: null handle");
+    DeviceGuard g(m->device);
+    m->timing = enable != 0;
+    m->ev_n = 0;
+    m->gemm_flops = 0;
+    if (m->timing && m->ev.empty()) {
+        m->ev.resize(4096);
+        for (auto &e : m->ev) CB_CUDA(cudaEventCreate(&e));
+    }
+    return CB_OK;
+}
+
+int cb_clip_timing_read(cb_clip *m, double *gemm_ms_total, double *gemm_flops, int *n_gemms) {
+    CB_REQUIRE(m && gemm_ms_total && gemm_flops && n_gemms, "cb_clip_timing_read: null argument");
+    DeviceGuard g(m->device);
+    double tot = 0;
+    for (int i = 0; i + 1 < m->ev_n; i += 2) {
+        CB_CUDA(cudaEventSynchronize(m->ev[i + 1]));
+        float ms = 0;
+        CB_CUDA(cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]));
+        tot += ms;
+    }
+    *gemm_ms_total = tot;
+    *gemm_flops = m->gemm_flops;
+    *n_gemms = m->ev_n / 2;
+    m->ev_n = 0;
+    m->gemm_flops = 0;
+    return CB_OK;
+}
+
+// ---- building blocks exported for unit tests ------------------------------------------
+int cb_layernorm_f16_device(const void *in, void *out, const float *gamma, const float *beta, int rows, int width,
+                            int in_row_stride, const int *gather, const float *cls_fill, int cls_period,
+                            void *stream) {
+    CB_REQUIRE(in && out && gamma && beta, "cb_layernorm_f16_device: null buffer");
+    return layernorm_f16((const __half *)in, (__half *)out, gamma, beta, rows, width, in_row_stride, gather, cls_fill,
+                         cls_period, (cudaStream_t)stream);
+}
+int cb_attention_f16_device(const void *qkv, void *out, int B, int L, int heads, int causal, void *stream) {
+    CB_REQUIRE(qkv && out, "cb_attention_f16_device: null buffer");
+    return attention_f16((const __half *)qkv, (__half *)out, B, L, heads, causal != 0, (cudaStream_t)stream);
+}
+int cb_preprocess_u8_device(const uint8_t *hwc, void *patches_f16, int B, void *stream) {
+    CB_REQUIRE(hwc && patches_f16, "cb_preprocess_u8_device: null buffer");
+    return preprocess_u8(hwc, (__half *)patches_f16, B, (cudaStream_t)stream);
+}
+int cb_preprocess_f32_device(const float *nchw, void *patches_f16, int B, void *stream) {
+    CB_REQUIRE(nchw && patches_f16, "cb_preprocess_f32_device: null buffer");
+    return preprocess_f32(nchw, (__half *)patches_f16, B, (cudaStream_t)stream);
+}
+int cb_l2norm_f32_device(const float *in, float *out, int rows, int width, void *stream) {
+    CB_REQUIRE(in && out, "cb_l2norm_f32_device: null buffer");
+    return l2norm_rows_f32(in, out, rows, width, (cudaStream_t)stream);
+}
+
+}  // extern "C"

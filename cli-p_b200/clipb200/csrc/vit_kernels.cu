@@ -1,0 +1,227 @@
+// HBM/L2-bound helper kernels of the CLIP towers: preprocess (clip._transform's
+// ToTensor+Normalize, written straight into patch-major im2col layout), LayerNorm
+// (fp32 statistics, as openai/CLIP's LayerNorm subclass does), row L2-normalise
+// (/root/reference/build-index.py:50), token-embedding gather (CLIP.encode_text).
+// All vectorised to 128-bit accesses, one warp per row, warp-shuffle reductions.
+#include "common.cuh"
+#include "vit_kernels.cuh"
+
+namespace cb {
+namespace {
+
+#define K_MEAN0 0.48145466f
+#define K_MEAN1 0.4578275f
+#define K_MEAN2 0.40821073f
+#define K_STD0 0.26862954f
+#define K_STD1 0.26130258f
+#define K_STD2 0.27577711f
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// one thread = 8 consecutive bytes of one image row (672 B = 84 chunks); 12 consecutive
+// threads cover one 32-pixel patch row = 96 contiguous output halfs
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t *__restrict__ img,
+                                                           __half *__restrict__ patches, int B) {
+    const int64_t total = (int64_t)B * 224 * 84;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int xb = (int)(t % 84);
+        const int y = (int)((t / 84) % 224);
+        const int b = (int)(t / (84 * 224));
+        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(img + ((size_t)(b * 224 + y) * 224) * 3) + xb);
+        const uint8_t *px = reinterpret_cast<const uint8_t *>(&raw);
+        float f[8];
+        int c = (xb * 8) % 3;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float mean = c == 0 ? K_MEAN0 : (c == 1 ? K_MEAN1 : K_MEAN2);
+            const float sd = c == 0 ? K_STD0 : (c == 1 ? K_STD1 : K_STD2);
+            f[e] = __fdiv_rn(__fdiv_rn((float)px[e], 255.0f) - mean, sd);
+            c = c == 2 ? 0 : c + 1;
+        }
+        const int gy = y >> 5, py = y & 31, gx = xb / 12, j = xb - gx * 12;
+        __half *dst = patches + ((size_t)(b * 49 + gy * 7 + gx)) * 3072 + py * 96 + j * 8;
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+}
+
+// one thread = 4 pixels x 3 channels of an NCHW fp32 image
+__global__ void __launch_bounds__(256) preprocess_f32_kernel(const float *__restrict__ img,
+                                                            __half *__restrict__ patches, int B) {
+    const int64_t total = (int64_t)B * 224 * 56;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int x4 = (int)(t % 56);
+        const int y = (int)((t / 56) % 224);
+        const int b = (int)(t / (56 * 224));
+        float4 ch[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            ch[c] = __ldg(reinterpret_cast<const float4 *>(img + (((size_t)b * 3 + c) * 224 + y) * 224) + x4);
+        const int gy = y >> 5, py = y & 31, gx = (x4 * 4) >> 5, px0 = (x4 * 4) & 31;
+        __half *dst = patches + ((size_t)(b * 49 + gy * 7 + gx)) * 3072 + py * 96 + px0 * 3;
+        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+        d2[0] = make_uint2(pack2(ch[0].x, ch[1].x), pack2(ch[2].x, ch[0].y));
+        d2[1] = make_uint2(pack2(ch[1].y, ch[2].y), pack2(ch[0].z, ch[1].z));
+        d2[2] = make_uint2(pack2(ch[2].z, ch[0].w), pack2(ch[1].w, ch[2].w));
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict__ in, __half *__restrict__ out,
+                                                       const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                       int rows, int in_row_stride, const int *__restrict__ gather,
+                                                       const float *__restrict__ cls_fill, int cls_period) {
+    constexpr int NV = W / 256;     // uint4 (8 halfs) per lane
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int64_t in_row = gather ? (int64_t)gather[row] : (int64_t)row * in_row_stride;
+    float v[NV * 8];
+    if (cls_fill != nullptr && (in_row % cls_period) == 0) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            const float4 *p = reinterpret_cast<const float4 *>(cls_fill + (lane + 32 * c) * 8);
+            float4 a = __ldg(p), b = __ldg(p + 1);
+            v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = a.z; v[c * 8 + 3] = a.w;
+            v[c * 8 + 4] = b.x; v[c * 8 + 5] = b.y; v[c * 8 + 6] = b.z; v[c * 8 + 7] = b.w;
+        }
+    } else {
+        const uint4 *p = reinterpret_cast<const uint4 *>(in + in_row * W);
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            uint4 u = p[lane + 32 * c];
+            const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float2 f = __half22float2(h[e]);
+                v[c * 8 + 2 * e] = f.x;
+                v[c * 8 + 2 * e + 1] = f.y;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; i++) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / W);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; i++) { float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + 1e-5f);
+    uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)row * W);
+#pragma unroll
+    for (int c = 0; c < NV; c++) {
+        const int col = (lane + 32 * c) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + col) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + col)), b1 = __ldg(reinterpret_cast<const float4 *>(beta + col) + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float r[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) r[e] = fmaf((v[c * 8 + e] - mean) * rstd, g[e], bb[e]);
+        o[lane + 32 * c] = make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+    }
+}
+
+__global__ void __launch_bounds__(256) l2norm_kernel(const float *__restrict__ in, float *__restrict__ out, int rows,
+                                                    int width) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4 *p = reinterpret_cast<const float4 *>(in + (size_t)row * width);
+    float4 *o = reinterpret_cast<float4 *>(out + (size_t)row * width);
+    const int n4 = width / 4;
+    float s = 0.f;
+    for (int i = lane; i < n4; i += 32) {
+        float4 f = p[i];
+        s = fmaf(f.x, f.x, s); s = fmaf(f.y, f.y, s); s = fmaf(f.z, f.z, s); s = fmaf(f.w, f.w, s);
+    }
+    const float inv = 1.0f / sqrtf(warp_sum(s));
+    for (int i = lane; i < n4; i += 32) {
+        float4 f = p[i];
+        o[i] = make_float4(f.x * inv, f.y * inv, f.z * inv, f.w * inv);
+    }
+}
+
+// one block per text row (77 tokens), one warp per token in turn
+__global__ void __launch_bounds__(256) text_embed_kernel(const int32_t *__restrict__ ids, const float *__restrict__ tok,
+                                                        const float *__restrict__ pos, __half *__restrict__ x,
+                                                        int *__restrict__ eot_row, int ctx, int width, int vocab) {
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int32_t *row = ids + (size_t)b * ctx;
+    if (warp == 0) {
+        int best = INT_MIN, best_t = 0;
+        for (int t = lane; t < ctx; t += 32) {
+            int v = row[t];
+            if (v > best) { best = v; best_t = t; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int ov = __shfl_xor_sync(0xffffffffu, best, o), ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+            if (ov > best || (ov == best && ot < best_t)) { best = ov; best_t = ot; }
+        }
+        if (lane == 0) eot_row[b] = b * ctx + best_t;
+    }
+    const int n4 = width / 4;
+    for (int t = warp; t < ctx; t += nwarp) {
+        int id = row[t];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const float4 *e = reinterpret_cast<const float4 *>(tok + (size_t)id * width);
+        const float4 *p = reinterpret_cast<const float4 *>(pos + (size_t)t * width);
+        uint2 *o = reinterpret_cast<uint2 *>(x + ((size_t)b * ctx + t) * width);
+        for (int i = lane; i < n4; i += 32) {
+            float4 a = __ldg(e + i), c = __ldg(p + i);
+            o[i] = make_uint2(pack2(a.x + c.x, a.y + c.y), pack2(a.z + c.z, a.w + c.w));
+        }
+    }
+}
+
+inline int grid_for(int64_t threads, int block) {
+    return (int)std::min<int64_t>((threads + block - 1) / block, (int64_t)kNumSMs * 16);
+}
+
+}  // namespace
+
+int preprocess_u8(const uint8_t *img, __half *patches, int B, cudaStream_t s) {
+    preprocess_u8_kernel<<<grid_for((int64_t)B * 224 * 84, 256), 256, 0, s>>>(img, patches, B);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+int preprocess_f32(const float *img, __half *patches, int B, cudaStream_t s) {
+    preprocess_f32_kernel<<<grid_for((int64_t)B * 224 * 56, 256), 256, 0, s>>>(img, patches, B);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+int layernorm_f16(const __half *in, __half *out, const float *gamma, const float *beta, int rows, int width,
+                  int in_row_stride, const int *gather, const float *cls_fill, int cls_period, cudaStream_t s) {
+    CB_REQUIRE(width == 768 || width == 512, "layernorm_f16: width %d not supported", width);
+    if (rows == 0) return CB_OK;
+    const int grid = (rows + 7) / 8;
+    if (cls_period <= 0) cls_period = 1;
+    if (width == 768)
+        layernorm_kernel<768><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period);
+    else
+        layernorm_kernel<512><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+int l2norm_rows_f32(const float *in, float *out, int rows, int width, cudaStream_t s) {
+    CB_REQUIRE(width % 4 == 0, "l2norm_rows_f32: width must be a multiple of 4");
+    if (rows == 0) return CB_OK;
+    l2norm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, out, rows, width);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+int text_embed(const int32_t *ids, const float *tok_emb, const float *pos_emb, __half *x, int *eot_row, int B,
+               int ctx, int width, int vocab, cudaStream_t s) {
+    if (B == 0) return CB_OK;
+    text_embed_kernel<<<B, 256, 0, s>>>(ids, tok_emb, pos_emb, x, eot_row, ctx, width, vocab);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+}  // namespace cb

@@ -101,6 +101,61 @@ const void *cb_flatip_device_rows(const cb_index *ix);
 int cb_flatip_timing(cb_index *ix, int enable);
 int cb_flatip_timing_read(cb_index *ix, double *scan_ms_total, int *n_scans);
 
+/* ---- CLIP ViT-B/32 towers (replaces `import clip`'s model) ----------------- */
+typedef struct cb_clip cb_clip;
+
+/* model, transform = clip.load("ViT-B/32", device, jit=False)
+ *                                   build-index.py:18, query-index.py:21
+ * Creates an empty model on CUDA device `device` with activation workspace for
+ * up to max_image_batch images / max_text_batch token rows per forward (larger
+ * calls are processed in chunks).  Parameters are then supplied by their
+ * openai/CLIP state-dict names as host float32 arrays (cb_clip_set_param; GEMM
+ * weights are stored as fp16, everything else fp32, like clip.load does on a
+ * CUDA device) and checked by cb_clip_finalize (all 302 tensors present with
+ * ViT-B/32 shapes). */
+int cb_clip_create(int device, int max_image_batch, int max_text_batch, cb_clip **out);
+int cb_clip_set_param(cb_clip *m, const char *name, const float *data_host, int64_t numel);
+int cb_clip_finalize(cb_clip *m);
+void cb_clip_free(cb_clip *m);
+
+/* image_features = model.encode_image(image)            build-index.py:49
+ * (+ `/ image_features.norm(dim=-1, keepdim=True)`      build-index.py:50  when normalize != 0)
+ * _u8 : B x 224 x 224 x 3 uint8 HWC pixels; clip._transform's ToTensor +
+ *       Normalize(mean, std) run on the GPU, fused with the im2col that feeds the
+ *       patch-embedding GEMM (build-index.py:48 for inputs that are already 224x224).
+ * _f32: B x 3 x 224 x 224 float32 NCHW, exactly what `transform(image)` returns
+ *       (the unchanged reference call).
+ * out : B x 512 float32. */
+int cb_clip_encode_image_u8_device(cb_clip *m, int64_t B, const uint8_t *hwc_dev, float *out_dev,
+                                   int normalize, void *stream);
+int cb_clip_encode_image_f32_device(cb_clip *m, int64_t B, const float *nchw_dev, float *out_dev,
+                                    int normalize, void *stream);
+int cb_clip_encode_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host,
+                            int normalize);
+
+/* text_features = model.encode_text(texts)              query-index.py:108
+ * ids: B x 77 int32 tokens as produced by clip.tokenize (query-index.py:107);
+ * the EOT position is argmax(ids) per row. out: B x 512 float32. */
+int cb_clip_encode_text_device(cb_clip *m, int64_t B, const int32_t *ids_dev, float *out_dev,
+                               int normalize, void *stream);
+int cb_clip_encode_text(cb_clip *m, int64_t B, const int32_t *ids_host, float *out_host,
+                        int normalize);
+
+/* live timing of the GEMM launches inside encode_* (bench.py roofline): summed
+ * CUDA-event duration, algorithmic FLOPs (2*M*N*K) and count since enable/read */
+int cb_clip_timing(cb_clip *m, int enable);
+int cb_clip_timing_read(cb_clip *m, double *gemm_ms_total, double *gemm_flops, int *n_gemms);
+
+/* building blocks of the towers, exported for unit tests (device pointers) */
+int cb_layernorm_f16_device(const void *in, void *out, const float *gamma, const float *beta,
+                            int rows, int width, int in_row_stride, const int *gather,
+                            const float *cls_fill, int cls_period, void *stream);
+int cb_attention_f16_device(const void *qkv, void *out, int B, int L, int heads, int causal,
+                            void *stream);
+int cb_preprocess_u8_device(const uint8_t *hwc, void *patches_f16, int B, void *stream);
+int cb_preprocess_f32_device(const float *nchw, void *patches_f16, int B, void *stream);
+int cb_l2norm_f32_device(const float *in, float *out, int rows, int width, void *stream);
+
 /* ---- tcgen05 GEMM building block (exported for unit tests and benches) ----
  * C[M,N] = epilogue(A[M,K] fp16 row-major x W[N,K]^T fp16 row-major), fp32
  * accumulation in tensor memory.  Replaces the cuBLAS calls torch dispatches for
