@@ -299,11 +299,16 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["embed", "search"])
+    ap.add_argument("--workload", default=None, choices=["embed", "search", "both"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local = dist_env()
-    workload = args.workload or ("embed" if embed_available() else "search")
+    # default: the headline line is the embed workload (BASELINE configs[1]); the search half
+    # of BASELINE's metric rides along in the same JSON line under "search"
+    workload = args.workload or ("both" if embed_available() else "search")
+    both = workload == "both"
+    if both:
+        workload = "embed"
     if args.steps is None:
         args.steps = 20 if workload == "embed" else 200
     if args.warmup is None:
@@ -360,6 +365,20 @@ def main():
                 else:
                     from clipb200 import clip
                     line["cpu_baseline"] = clip.bench_hooks()["cpu_baseline"]()
+        if both:
+            import copy
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            sargs = copy.copy(args)
+            sargs.steps, sargs.warmup = 10 * args.steps, max(3, 4 * args.warmup)
+            sres, sclocks = run_search(sargs, torch, dist, rank, world, local)
+            if rank == 0:
+                sres.update({"steps": sargs.steps, "warmup": sargs.warmup, "clocks": sclocks, "n_gpus": world})
+                if world == 1 and not args.no_cpu_baseline:
+                    sres["cpu_baseline"] = cpu_search_baseline()
+                line["search"] = sres
+        if rank == 0:
             print(json.dumps(line))
     finally:
         if world > 1:

@@ -30,10 +30,14 @@ struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
+    static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : 5);
     static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+    // epilogue staging: per epilogue warp 32 rows x BN fp16, rows padded by 16 B so that both
+    // the row-per-thread accesses and the row-contiguous accesses are bank-conflict free
+    static constexpr int EPI_ROW_BYTES = BN * 2 + 16;
+    static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + 1024;  // + alignment slack
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -139,6 +143,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -233,24 +252,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         const int q = warp & 3;                          // TMEM lane quadrant this warp may touch
         uint32_t as = 0, aphase = 0;
+        constexpr int CPR = BN / 8;                      // 16-byte chunks per staged row
+        const uint32_t stage_base = smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + q * C::EPI_WARP_BYTES;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int row0 = m_blk * BM + q * 32;        // first row of this warp's slice
+            const int row = row0 + lane;
+            const bool row_ok = row < g.M;
+            const int n_base = n_blk * BN;
+            if (EPI == EPI_BIAS_RESID) {
+                // prefetch this warp's residual slice (32 rows x BN) with coalesced 16-byte
+                // cp.async while the tile's MMAs are still running
+                for (int c = lane; c < 32 * CPR; c += 32) {
+                    const int r = c / CPR, j = c - r * CPR;
+                    if (row0 + r < g.M)
+                        cp_async16(stage_base + r * C::EPI_ROW_BYTES + j * 16,
+                                   g.resid + (size_t)(row0 + r) * g.N + n_base + j * 8);
+                }
+            }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const int row = m_blk * BM + q * 32 + lane;
-            const bool row_ok = row < g.M;
-            int out_row = row;
+            if (EPI == EPI_BIAS_RESID) {
+                cp_async_wait_all();
+                __syncwarp();
+            }
             const float *pos_row = nullptr;
             if (EPI == EPI_PATCH) {
                 const int img = row / 49, p = row - img * 49;
-                out_row = row + img + 1;
                 pos_row = g.pos + (size_t)(1 + p) * g.N;
             }
+            const uint32_t my_row_smem = stage_base + lane * C::EPI_ROW_BYTES;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, v);
-                const int n0 = n_blk * BN + c * 32;
+                const int n0 = n_base + c * 32;
                 float add[32];
                 if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) {
                     if (g.bias) {
@@ -277,9 +313,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 uint4 rz[4];
                 if (EPI == EPI_BIAS_RESID) {
-                    const uint4 *r4 = reinterpret_cast<const uint4 *>(g.resid + (size_t)row * g.N + n0);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) rz[j] = row_ok ? r4[j] : make_uint4(0, 0, 0, 0);
+                    for (int j = 0; j < 4; j++) rz[j] = lds128(my_row_smem + c * 64 + j * 16);
                 }
                 tmem_ld_wait();
                 float o[32];
@@ -301,25 +336,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                 }
-                if (row_ok) {
-                    if (EPI == EPI_F32) {
-                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.C) + (size_t)out_row * g.ldc + n0);
+                if (EPI == EPI_F32) {
+                    if (row_ok) {
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.C) + (size_t)row * g.ldc + n0);
 #pragma unroll
                         for (int j = 0; j < 8; j++) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                    } else {
-                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(g.C) + (size_t)out_row * g.ldc + n0);
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            dst[j] = make_uint4(pack_h2(o[8 * j], o[8 * j + 1]), pack_h2(o[8 * j + 2], o[8 * j + 3]),
-                                                pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7]));
                     }
+                } else {
+                    // stage the fp16 row slice; the coalesced copy-out happens after the loop
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        sts128(my_row_smem + c * 64 + j * 16,
+                               make_uint4(pack_h2(o[8 * j], o[8 * j + 1]), pack_h2(o[8 * j + 2], o[8 * j + 3]),
+                                          pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7])));
                 }
             }
+            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);     // accumulator stage drained
+            if (lane == 0) mbar_arrive(&tempty[as]);
             as ^= 1;
             if (as == 0) aphase ^= 1;
+            if (EPI != EPI_F32) {
+                // coalesced copy-out: consecutive lanes write consecutive 16-byte chunks of a row
+                __half *Cb = reinterpret_cast<__half *>(g.C);
+                for (int c = lane; c < 32 * CPR; c += 32) {
+                    const int r = c / CPR, j = c - r * CPR;
+                    const int grow = row0 + r;
+                    if (grow < g.M) {
+                        int orow = grow;
+                        if (EPI == EPI_PATCH) orow = grow + grow / 49 + 1;
+                        const uint4 val = lds128(stage_base + r * C::EPI_ROW_BYTES + j * 16);
+                        *reinterpret_cast<uint4 *>(Cb + (size_t)orow * g.ldc + n_base + j * 8) = val;
+                    }
+                }
+                __syncwarp();                            // staging buffer is reused by the next tile
+            }
         }
     }
 
