@@ -1,6 +1,16 @@
 // Hand-written tcgen05 GEMM (sm_100a): TMA -> 128B-swizzled smem ring -> tcgen05.mma
-// (cta_group::1, kind::f16, M=128 x N=BN x K=16) -> fp32 accumulators in TMEM (double
-// buffered) -> tcgen05.ld epilogue fused with bias / QuickGELU / residual / pos-emb.
+// (kind::f16, K=16 per instruction) -> fp32 accumulators in TMEM (double buffered) ->
+// tcgen05.ld epilogue fused with bias / QuickGELU / residual / pos-emb, staged through
+// shared memory so global stores (and the residual read) are row-coalesced.
+//
+// Two flavours of the same kernel (template NCTA):
+//   NCTA = 2  cta_group::2: a cluster of two CTAs (one SM pair) computes a 256 x BN tile.
+//             Each CTA TMA-loads its own 128 rows of A and HALF of the W tile; the leader
+//             CTA issues one M=256 MMA that reads both halves, so per-SM L2->smem operand
+//             traffic drops from 16+BN/8 KB to 16+BN/16 KB per k-block.  Used for the big
+//             tower GEMMs (the 1-CTA form is operand-bandwidth bound at ~60 % tensor pipe).
+//   NCTA = 1  cta_group::1, 128 x BN tile per CTA: small problems (M <= 128 rows or fewer
+//             tiles than SM pairs).
 //
 // Replaces the cuBLAS/cuDNN calls torch dispatches for openai/CLIP's conv1, in_proj,
 // out_proj, c_fc, c_proj, proj  (reference
@@ -10,7 +20,8 @@
 // running CTAs share A tiles through L2).  Warp roles (192 threads):
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  epilogue; warp w owns TMEM lanes 32*(w%4) .. +31  (= tile rows)
+//   warps 2..9  epilogue; warp w owns TMEM lanes 32*(w%4) .. +31 (= tile rows) and the
+//               column half (w-2)/4 of the tile
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -22,22 +33,31 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 fp16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant, each owns half of the tile's columns
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t kSpinLimit = 1u << 28;   // turns a protocol bug into a trap, not a hang
 
-template <int BN>
+template <int BN, int NCTA>
 struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_ROWS = BN / NCTA;                  // rows of W this CTA loads per k-block
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : 5);
     static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
     static constexpr int BAR_BYTES = 256;
-    // epilogue staging: per epilogue warp 32 rows x BN fp16, rows padded by 16 B so that both
-    // the row-per-thread accesses and the row-contiguous accesses are bank-conflict free
-    static constexpr int EPI_ROW_BYTES = BN * 2 + 16;
-    static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + 1024;  // + alignment slack
+    // epilogue staging: per epilogue warp 32 rows x BN/2 fp16, rows padded by 16 B so that both
+    // the row-per-thread accesses and the row-contiguous accesses are bank-conflict free,
+    // followed by the warp's BN/2 fp32 bias (or zero) values
+    static constexpr int EPI_COLS = BN / 2;
+    static constexpr int EPI_ROW_BYTES = EPI_COLS * 2 + 16;
+    static constexpr int EPI_BIAS_OFF = 32 * EPI_ROW_BYTES;
+    static constexpr int EPI_WARP_BYTES = EPI_BIAS_OFF + EPI_COLS * 4;
+    static constexpr int kMaxSmem = 232448;                   // 227 KB opt-in limit
+    static constexpr int FIXED = BAR_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024;   // + alignment slack
+    static constexpr int STAGES_FIT = (kMaxSmem - FIXED) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+    static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -53,6 +73,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the TMEM-drained signal orders only tcgen05.ld results (already waited for), not memory
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -85,32 +109,90 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// 2-CTA TMA load: data lands in this CTA's smem, completion bytes are credited to the
+// LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                                uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+template <int NCTA>
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (NCTA == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
 }
+template <int NCTA>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    if (NCTA == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]; both operands K-major
+template <int NCTA>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (NCTA == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
-// arrive on an mbarrier once all previously issued MMAs have completed
+// arrive on an mbarrier once all previously issued MMAs have completed; with NCTA = 2 the
+// arrive is multicast to the barrier at the same offset in both CTAs of the pair
+template <int NCTA>
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+    if (NCTA == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                     : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+            : "memory");
+    }
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t gets row (lane base + t)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -164,11 +246,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs g, const int m_tiles, const int n_tiles) {
-    using C = Cfg<BN>;
+    // m_tiles counts (128*NCTA)-row tiles; a cluster of NCTA CTAs owns one tile at a time
+    using C = Cfg<BN, NCTA>;
+    const uint32_t cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x / NCTA, num_clusters = gridDim.x / NCTA;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
@@ -192,15 +278,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             for (int i = 0; i < 2; i++) {
                 mbar_init(&tfull[i], 1);
-                mbar_init(&tempty[i], 4);      // one arrive per epilogue warp
+                mbar_init(&tempty[i], kEpiWarps * NCTA);   // one arrive per epilogue warp of every CTA
             }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, C::TMEM_COLS);
+        tmem_alloc<NCTA>(tmem_slot, C::TMEM_COLS);
     }
     tc_fence_before();
     __syncthreads();
+    if (NCTA > 1) cluster_sync_all();          // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
@@ -210,23 +297,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                     uint8_t *sa = smem + stage * C::STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
-                    tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN, &full[stage]);
+                    if (NCTA == 1) {
+                        mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
+                        tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN, &full[stage]);
+                    } else {
+                        // both CTAs' bytes are credited to the leader's barrier
+                        if (leader) mbar_expect_tx(&full[stage], NCTA * C::STAGE_BYTES);
+                        tma_load_2d_2sm(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
+                        tma_load_2d_2sm(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN + (int)cta_rank * C::B_ROWS,
+                                        &full[stage]);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc(BM * NCTA, BN);
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -239,30 +334,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         // advance 16 elements = 32 B along K inside the swizzle atom: +2 in 16-B units
-                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_f16<NCTA>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);          // frees the smem slot when the MMAs retire
+                    umma_commit<NCTA>(&empty[stage]);    // frees the smem slot (in both CTAs) when the MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[as]);                 // accumulator complete -> epilogue
+                umma_commit<NCTA>(&tfull[as]);           // accumulator complete -> epilogue (both CTAs)
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }
         }
     } else {
         const int q = warp & 3;                          // TMEM lane quadrant this warp may touch
+        const int half = (warp - 2) >> 2;                // which half of the tile's columns
         uint32_t as = 0, aphase = 0;
-        constexpr int CPR = BN / 8;                      // 16-byte chunks per staged row
-        const uint32_t stage_base = smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + q * C::EPI_WARP_BYTES;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        constexpr int EC = C::EPI_COLS;                  // columns per epilogue warp
+        constexpr int CPR = EC / 8;                      // 16-byte chunks per staged row
+        const uint32_t stage_base = smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) +
+                                    (uint32_t)(warp - 2) * C::EPI_WARP_BYTES;
+        const uint32_t bias_smem = stage_base + C::EPI_BIAS_OFF;
+        const uint32_t my_row_smem = stage_base + lane * C::EPI_ROW_BYTES;
+        constexpr bool kHasBias = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
             const int row0 = m_blk * BM + q * 32;        // first row of this warp's slice
             const int row = row0 + lane;
             const bool row_ok = row < g.M;
-            const int n_base = n_blk * BN;
+            const int n_base = n_blk * BN + half * EC;   // first column of this warp's slice
+            // -- before the accumulator is ready: stage bias and (coalesced, async) the residual
+            if (kHasBias) {
+                for (int j = lane; j < EC / 4; j += 32) {
+                    float4 b = g.bias ? __ldg(reinterpret_cast<const float4 *>(g.bias + n_base) + j) : make_float4(0, 0, 0, 0);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(bias_smem + j * 16), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+                }
+            }
             if (EPI == EPI_BIAS_RESID) {
-                // prefetch this warp's residual slice (32 rows x BN) with coalesced 16-byte
-                // cp.async while the tile's MMAs are still running
+#pragma unroll 4
                 for (int c = lane; c < 32 * CPR; c += 32) {
                     const int r = c / CPR, j = c - r * CPR;
                     if (row0 + r < g.M)
@@ -272,33 +379,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            if (EPI == EPI_BIAS_RESID) {
-                cp_async_wait_all();
-                __syncwarp();
-            }
+            if (EPI == EPI_BIAS_RESID) cp_async_wait_all();
+            __syncwarp();
             const float *pos_row = nullptr;
             if (EPI == EPI_PATCH) {
                 const int img = row / 49, p = row - img * 49;
                 pos_row = g.pos + (size_t)(1 + p) * g.N;
             }
-            const uint32_t my_row_smem = stage_base + lane * C::EPI_ROW_BYTES;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            for (int c = 0; c < EC / 32; c++) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, v);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * EC + c * 32, v);
                 const int n0 = n_base + c * 32;
                 float add[32];
-                if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) {
-                    if (g.bias) {
-                        const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + n0);
+                if (kHasBias) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            float4 b = __ldg(b4 + j);
-                            add[4 * j] = b.x; add[4 * j + 1] = b.y; add[4 * j + 2] = b.z; add[4 * j + 3] = b.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) add[j] = 0.f;
+                    for (int j = 0; j < 8; j++) {
+                        float4 b;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_smem + c * 128 + j * 16));
+                        add[4 * j] = b.x; add[4 * j + 1] = b.y; add[4 * j + 2] = b.z; add[4 * j + 3] = b.w;
                     }
                 } else if (EPI == EPI_PATCH) {
                     const float4 *p4 = reinterpret_cast<const float4 *>(pos_row + n0);
@@ -354,21 +453,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                if (NCTA == 1) mbar_arrive_relaxed(&tempty[as]);
+                else mbar_arrive_cluster(&tempty[as], 0);    // the leader's MMA warp waits for both CTAs
+            }
             as ^= 1;
             if (as == 0) aphase ^= 1;
             if (EPI != EPI_F32) {
                 // coalesced copy-out: consecutive lanes write consecutive 16-byte chunks of a row
                 __half *Cb = reinterpret_cast<__half *>(g.C);
-                for (int c = lane; c < 32 * CPR; c += 32) {
-                    const int r = c / CPR, j = c - r * CPR;
-                    const int grow = row0 + r;
-                    if (grow < g.M) {
-                        int orow = grow;
-                        if (EPI == EPI_PATCH) orow = grow + grow / 49 + 1;
-                        const uint4 val = lds128(stage_base + r * C::EPI_ROW_BYTES + j * 16);
-                        *reinterpret_cast<uint4 *>(Cb + (size_t)orow * g.ldc + n_base + j * 8) = val;
+                constexpr int ITERS = CPR;               // 32*CPR chunks / 32 lanes
+#pragma unroll
+                for (int i0 = 0; i0 < ITERS; i0 += 4) {
+                    uint4 val[4];
+                    int orow[4], jj[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int c = (i0 + u) * 32 + lane;
+                        const int r = c / CPR, j = c - r * CPR;
+                        const int grow = row0 + r;
+                        jj[u] = j;
+                        orow[u] = grow < g.M ? (EPI == EPI_PATCH ? grow + grow / 49 + 1 : grow) : -1;
+                        val[u] = lds128(stage_base + r * C::EPI_ROW_BYTES + j * 16);
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (orow[u] >= 0)
+                            *reinterpret_cast<uint4 *>(Cb + (size_t)orow[u] * g.ldc + n_base + jj[u] * 8) = val[u];
                 }
                 __syncwarp();                            // staging buffer is reused by the next tile
             }
@@ -377,9 +488,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (NCTA > 1) cluster_sync_all();          // nobody exits while the peer may still touch its smem/TMEM
     if (warp == 1) {
         __syncwarp();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
+        tmem_dealloc<NCTA>(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -416,10 +528,10 @@ int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uin
     return CB_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA>
 int launch(const GemmArgs &g, cudaStream_t s) {
-    using C = Cfg<BN>;
-    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    using C = Cfg<BN, NCTA>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, NCTA>;
     static bool attr_done = false;
     if (!attr_done) {
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -428,45 +540,62 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
     if (rc) return rc;
-    rc = make_map(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, BN);
+    rc = make_map(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, C::B_ROWS);
     if (rc) return rc;
-    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN;
+    const int m_tiles = (g.M + BM * NCTA - 1) / (BM * NCTA), n_tiles = g.N / BN;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = std::min(m_tiles * n_tiles, sms);
-    kern<<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, g, m_tiles, n_tiles);
+    const int clusters = std::min(m_tiles * n_tiles, sms / NCTA);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * NCTA);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g, m_tiles, n_tiles));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
 
-template <int BN>
+template <int BN, int NCTA>
 int dispatch_epi(const GemmArgs &g, cudaStream_t s) {
     switch (g.epilogue) {
-        case EPI_BIAS: return launch<BN, EPI_BIAS>(g, s);
-        case EPI_BIAS_GELU: return launch<BN, EPI_BIAS_GELU>(g, s);
-        case EPI_BIAS_RESID: return launch<BN, EPI_BIAS_RESID>(g, s);
-        case EPI_PATCH: return launch<BN, EPI_PATCH>(g, s);
-        case EPI_F32: return launch<BN, EPI_F32>(g, s);
+        case EPI_BIAS: return launch<BN, EPI_BIAS, NCTA>(g, s);
+        case EPI_BIAS_GELU: return launch<BN, EPI_BIAS_GELU, NCTA>(g, s);
+        case EPI_BIAS_RESID: return launch<BN, EPI_BIAS_RESID, NCTA>(g, s);
+        case EPI_PATCH: return launch<BN, EPI_PATCH, NCTA>(g, s);
+        case EPI_F32: return launch<BN, EPI_F32, NCTA>(g, s);
     }
     set_error("gemm_f16: unknown epilogue %d", g.epilogue);
     return CB_ERR_INVALID;
 }
 
-// pick the N tile that wastes the fewest SM-rounds of the static persistent schedule
-int pick_bn(int M, int N, int sms) {
-    const int m_tiles = (M + BM - 1) / BM;
-    int best = 0;
+// Pick cluster size and N tile.  A CTA pair is used whenever the problem has more than one
+// 128-row block (it halves the W traffic per SM and measured faster on every tower shape,
+// profiles/r01_gemm_sweep.txt); the N tile is the one that minimises
+// rounds-of-the-static-schedule x tile width / measured relative tile efficiency.
+void pick_config(int M, int N, int sms, int *ncta_out, int *bn_out) {
+    const int ncta = M > BM ? 2 : 1;
+    const int m_tiles = (M + BM * ncta - 1) / (BM * ncta);
+    const int slots = sms / ncta;
     double best_cost = 1e30;
+    *ncta_out = ncta;
+    *bn_out = 128;
     for (int bn : {256, 192, 128}) {
         if (N % bn) continue;
         const int tiles = m_tiles * (N / bn);
-        const int rounds = (tiles + sms - 1) / sms;
-        // cost ~ rounds x tile width; narrow tiles pay more smem traffic per flop
-        double cost = (double)rounds * bn * (bn == 128 ? 1.08 : 1.0);
-        if (cost < best_cost) { best_cost = cost; best = bn; }
+        const int rounds = (tiles + slots - 1) / slots;
+        const double eff = bn == 256 ? 1.0 : (bn == 192 ? 0.90 : 0.66);
+        const double cost = (double)rounds * bn / eff;
+        if (cost < best_cost) { best_cost = cost; *bn_out = bn; }
     }
-    return best;
 }
 
 }  // namespace
@@ -483,15 +612,28 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int bn = pick_bn(g.M, g.N, sms);
+    int ncta = 1, bn = 128;
+    pick_config(g.M, g.N, sms, &ncta, &bn);
     if (const char *e = getenv("CLIPB200_GEMM_BN")) {
         int v = atoi(e);
         if ((v == 128 || v == 192 || v == 256) && g.N % v == 0) bn = v;
     }
-    switch (bn) {
-        case 256: return dispatch_epi<256>(g, stream);
-        case 192: return dispatch_epi<192>(g, stream);
-        case 128: return dispatch_epi<128>(g, stream);
+    if (const char *e = getenv("CLIPB200_GEMM_NCTA")) {
+        int v = atoi(e);
+        if (v == 1 || (v == 2 && g.M > BM)) ncta = v;
+    }
+    if (ncta == 2) {
+        switch (bn) {
+            case 256: return dispatch_epi<256, 2>(g, stream);
+            case 192: return dispatch_epi<192, 2>(g, stream);
+            case 128: return dispatch_epi<128, 2>(g, stream);
+        }
+    } else {
+        switch (bn) {
+            case 256: return dispatch_epi<256, 1>(g, stream);
+            case 192: return dispatch_epi<192, 1>(g, stream);
+            case 128: return dispatch_epi<128, 1>(g, stream);
+        }
     }
     set_error("gemm_f16: no tile shape for N=%d", g.N);
     return CB_ERR_INVALID;

@@ -45,12 +45,15 @@ def test_bias_epilogue(M, N, K):
     _close(torch, out, ref)
 
 
+@pytest.mark.parametrize("ncta", ["1", "2"])
 @pytest.mark.parametrize("bn", ["128", "192", "256"])
-def test_all_tile_widths(bn, monkeypatch):
+def test_all_tile_widths(bn, ncta, monkeypatch):
+    """Every (cluster size, N tile) instantiation, incl. an M tail inside a CTA pair."""
     import torch
     monkeypatch.setenv("CLIPB200_GEMM_BN", bn)
+    monkeypatch.setenv("CLIPB200_GEMM_NCTA", ncta)
     g = torch.Generator(device="cuda").manual_seed(int(bn))
-    M, N, K = 1280, 768, 768
+    M, N, K = 1280 + 77, 768, 768
     A = (torch.randn((M, K), generator=g, device="cuda") * 0.5).half()
     W = (torch.randn((N, K), generator=g, device="cuda") * K ** -0.5).half()
     out = _gemm(torch, A, W, bias=None)
