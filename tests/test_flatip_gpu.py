@@ -243,3 +243,20 @@ def test_full_size_properties():
     # host-pointer entry point returns the same answer
     Dh, Ih = index.search(q.cpu().numpy(), k)
     assert (Ih == I.numpy()).all() and (Dh == D.numpy()).all()
+
+
+def test_two_physical_gpus_equal_one(db100k):
+    """Real multi-device sharding inside one process (the REPL's mode): needs >= 2 GPUs."""
+    import torch
+    from clipb200 import faiss
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    xq = synth.unit_rows(3, seed=7, clip_like=True)
+    one = faiss.IndexFlatIP(512, storage="f16", devices=[0])
+    two = faiss.IndexFlatIP(512, storage="f16", devices=[0, 1])
+    one.add(db100k)
+    two.add(db100k)
+    for k in (1, 100):
+        D0, I0 = one.search(xq, k)
+        D1, I1 = two.search(xq, k)
+        assert (I0 == I1).all() and (D0.view(np.uint32) == D1.view(np.uint32)).all()
