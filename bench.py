@@ -146,16 +146,21 @@ def timed_region(torch, dist, world, fn, steps, warmup, sampler=None):
     return ms / 1e3
 
 
-def timed_region_wall(torch, dist, world, fn, steps, warmup):
-    """Same bracket, host clock (for the synchronous host-buffer API)."""
+def timed_region_wall(torch, dist, world, fn, steps, warmup, drain=None):
+    """Same bracket, host clock (for the host-buffer API).  `drain` completes any work the
+    API call left in flight; it runs inside the timed region."""
     for _ in range(warmup):
         fn()
+    if drain:
+        drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
+    if drain:
+        drain()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:

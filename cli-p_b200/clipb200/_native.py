@@ -55,6 +55,8 @@ SIGNATURES = {
     "cb_clip_encode_image_u8_device": (_int, [_p, _i64, _p, _p, _int, _p]),
     "cb_clip_encode_image_f32_device": (_int, [_p, _i64, _p, _p, _int, _p]),
     "cb_clip_encode_image_u8": (_int, [_p, _i64, _p, _p, _int]),
+    "cb_clip_submit_image_u8": (_int, [_p, _i64, _p, _p, _int]),
+    "cb_clip_sync": (_int, [_p]),
     "cb_clip_encode_text_device": (_int, [_p, _i64, _p, _p, _int, _p]),
     "cb_clip_encode_text": (_int, [_p, _i64, _p, _p, _int]),
     "cb_clip_timing": (_int, [_p, _int]),

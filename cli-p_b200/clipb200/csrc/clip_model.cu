@@ -62,6 +62,13 @@ struct cb_clip {
     int32_t *d_ids = nullptr;
     float *d_out = nullptr;
     cudaStream_t stream = nullptr;
+    // pipelined host entry point: two input/output staging slots, copies on their own stream
+    cudaStream_t copy_stream = nullptr;
+    uint8_t *slot_img[2] = {nullptr, nullptr};
+    float *slot_out[2] = {nullptr, nullptr};
+    cudaEvent_t slot_copied[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    int next_slot = 0;
     // live GEMM timing (bench.py roofline)
     bool timing = false;
     std::vector<cudaEvent_t> ev;
@@ -247,6 +254,12 @@ void cb_clip_free(cb_clip *m) {
     void *bufs[] = {m->patches, m->x, m->h, m->qkv, m->att, m->mlp, m->cls, m->emb, m->eot, m->d_img, m->d_ids, m->d_out, m->cls_pos};
     for (void *p : bufs) cudaFree(p);
     for (cudaEvent_t ev : m->ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(m->slot_img[i]); cudaFree(m->slot_out[i]);
+        if (m->slot_copied[i]) cudaEventDestroy(m->slot_copied[i]);
+        if (m->slot_done[i]) cudaEventDestroy(m->slot_done[i]);
+    }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -385,6 +398,48 @@ int cb_clip_encode_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, floa
         CB_CUDA(cudaMemcpyAsync(out_host + lo * ED, m->d_out, (size_t)b * ED * 4, cudaMemcpyDeviceToHost, m->stream));
         CB_CUDA(cudaStreamSynchronize(m->stream));
     }
+    return CB_OK;
+}
+
+// Pipelined variant of cb_clip_encode_image_u8: returns as soon as the work is queued.  The
+// H2D copy of this batch runs on a copy stream and overlaps the forward pass of the previous
+// batch; results land in out_host after cb_clip_sync().  At most two batches are in flight
+// (two staging slots); host_in/out_host must stay valid (and should be pinned) until then.
+int cb_clip_submit_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host, int normalize) {
+    CLIP_READY(m, "cb_clip_submit_image_u8");
+    CB_REQUIRE(B > 0 && B <= m->max_img, "cb_clip_submit_image_u8: B must be in [1, max_image_batch]");
+    CB_REQUIRE(hwc_host && out_host, "cb_clip_submit_image_u8: null buffer");
+    DeviceGuard g(m->device);
+    const size_t img_bytes = 224 * 224 * 3;
+    if (!m->copy_stream) {
+        CB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CB_CUDA(cudaMalloc(&m->slot_img[i], (size_t)m->max_img * img_bytes));
+            CB_CUDA(cudaMalloc(&m->slot_out[i], (size_t)m->max_img * ED * 4));
+            CB_CUDA(cudaEventCreateWithFlags(&m->slot_copied[i], cudaEventDisableTiming));
+            CB_CUDA(cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int sl = m->next_slot;
+    m->next_slot ^= 1;
+    // the slot's previous forward pass must have consumed its input before we overwrite it
+    if (m->slot_used[sl]) CB_CUDA(cudaStreamWaitEvent(m->copy_stream, m->slot_done[sl], 0));
+    CB_CUDA(cudaMemcpyAsync(m->slot_img[sl], hwc_host, (size_t)B * img_bytes, cudaMemcpyHostToDevice, m->copy_stream));
+    CB_CUDA(cudaEventRecord(m->slot_copied[sl], m->copy_stream));
+    CB_CUDA(cudaStreamWaitEvent(m->stream, m->slot_copied[sl], 0));
+    int rc = cb_clip_encode_image_u8_device(m, B, m->slot_img[sl], m->slot_out[sl], normalize, m->stream);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(out_host, m->slot_out[sl], (size_t)B * ED * 4, cudaMemcpyDeviceToHost, m->stream));
+    CB_CUDA(cudaEventRecord(m->slot_done[sl], m->stream));
+    m->slot_used[sl] = true;
+    return CB_OK;
+}
+
+int cb_clip_sync(cb_clip *m) {
+    CB_REQUIRE(m != nullptr, "cb_clip_sync: null handle");
+    DeviceGuard g(m->device);
+    if (m->copy_stream) CB_CUDA(cudaStreamSynchronize(m->copy_stream));
+    CB_CUDA(cudaStreamSynchronize(m->stream));
     return CB_OK;
 }
 

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(256) preprocess_f32_kernel(const float *__rest
     }
 }
 
+// persistent warps: each warp walks rows with a stride and keeps the next row's loads in
+// flight while it reduces / writes the current one
 template <int W>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict__ in, __half *__restrict__ out,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -77,52 +79,75 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict
                                                        const float *__restrict__ cls_fill, int cls_period) {
     constexpr int NV = W / 256;     // uint4 (8 halfs) per lane
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int stride = gridDim.x * (blockDim.x >> 5);
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
-    const int64_t in_row = gather ? (int64_t)gather[row] : (int64_t)row * in_row_stride;
-    float v[NV * 8];
-    if (cls_fill != nullptr && (in_row % cls_period) == 0) {
-#pragma unroll
-        for (int c = 0; c < NV; c++) {
-            const float4 *p = reinterpret_cast<const float4 *>(cls_fill + (lane + 32 * c) * 8);
-            float4 a = __ldg(p), b = __ldg(p + 1);
-            v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = a.z; v[c * 8 + 3] = a.w;
-            v[c * 8 + 4] = b.x; v[c * 8 + 5] = b.y; v[c * 8 + 6] = b.z; v[c * 8 + 7] = b.w;
-        }
-    } else {
-        const uint4 *p = reinterpret_cast<const uint4 *>(in + in_row * W);
-#pragma unroll
-        for (int c = 0; c < NV; c++) {
-            uint4 u = p[lane + 32 * c];
-            const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                float2 f = __half22float2(h[e]);
-                v[c * 8 + 2 * e] = f.x;
-                v[c * 8 + 2 * e + 1] = f.y;
-            }
-        }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV * 8; i++) s += v[i];
-    const float mean = warp_sum(s) * (1.0f / W);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV * 8; i++) { float d = v[i] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + 1e-5f);
-    uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)row * W);
+
+    // per-lane slice of gamma / beta stays in registers across rows
+    float g[NV * 8], bt[NV * 8];
 #pragma unroll
     for (int c = 0; c < NV; c++) {
         const int col = (lane + 32 * c) * 8;
         const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + col) + 1);
         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + col)), b1 = __ldg(reinterpret_cast<const float4 *>(beta + col) + 1);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float r[8];
+        g[c * 8 + 0] = g0.x; g[c * 8 + 1] = g0.y; g[c * 8 + 2] = g0.z; g[c * 8 + 3] = g0.w;
+        g[c * 8 + 4] = g1.x; g[c * 8 + 5] = g1.y; g[c * 8 + 6] = g1.z; g[c * 8 + 7] = g1.w;
+        bt[c * 8 + 0] = b0.x; bt[c * 8 + 1] = b0.y; bt[c * 8 + 2] = b0.z; bt[c * 8 + 3] = b0.w;
+        bt[c * 8 + 4] = b1.x; bt[c * 8 + 5] = b1.y; bt[c * 8 + 6] = b1.z; bt[c * 8 + 7] = b1.w;
+    }
+    auto src_row = [&](int r) -> int64_t { return gather ? (int64_t)gather[r] : (int64_t)r * in_row_stride; };
+    auto load = [&](uint4 (&u)[NV], int64_t in_row) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(in + in_row * W);
 #pragma unroll
-        for (int e = 0; e < 8; e++) r[e] = fmaf((v[c * 8 + e] - mean) * rstd, g[e], bb[e]);
-        o[lane + 32 * c] = make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+        for (int c = 0; c < NV; c++) u[c] = p[lane + 32 * c];
+    };
+    uint4 cur[NV], nxt[NV];
+    int64_t cur_in = src_row(row);
+    load(cur, cur_in);
+    for (; row < rows; row += stride) {
+        const int nrow = row + stride;
+        int64_t nxt_in = 0;
+        if (nrow < rows) { nxt_in = src_row(nrow); load(nxt, nxt_in); }
+        float v[NV * 8];
+        if (cls_fill != nullptr && (cur_in % cls_period) == 0) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                const float4 *p = reinterpret_cast<const float4 *>(cls_fill + (lane + 32 * c) * 8);
+                float4 a = __ldg(p), b = __ldg(p + 1);
+                v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = a.z; v[c * 8 + 3] = a.w;
+                v[c * 8 + 4] = b.x; v[c * 8 + 5] = b.y; v[c * 8 + 6] = b.z; v[c * 8 + 7] = b.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&cur[c]);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    float2 f = __half22float2(h[e]);
+                    v[c * 8 + 2 * e] = f.x;
+                    v[c * 8 + 2 * e + 1] = f.y;
+                }
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV * 8; i++) s += v[i];
+        const float mean = warp_sum(s) * (1.0f / W);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV * 8; i++) { float d = v[i] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + 1e-5f);
+        uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)row * W);
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            float r[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) r[e] = fmaf((v[c * 8 + e] - mean) * rstd, g[c * 8 + e], bt[c * 8 + e]);
+            o[lane + 32 * c] = make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+        }
+#pragma unroll
+        for (int c = 0; c < NV; c++) cur[c] = nxt[c];
+        cur_in = nxt_in;
     }
 }
 
@@ -200,7 +225,7 @@ int layernorm_f16(const __half *in, __half *out, const float *gamma, const float
                   int in_row_stride, const int *gather, const float *cls_fill, int cls_period, cudaStream_t s) {
     CB_REQUIRE(width == 768 || width == 512, "layernorm_f16: width %d not supported", width);
     if (rows == 0) return CB_OK;
-    const int grid = (rows + 7) / 8;
+    const int grid = std::min((rows + 7) / 8, kNumSMs * 4);
     if (cls_period <= 0) cls_period = 1;
     if (width == 768)
         layernorm_kernel<768><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period);

@@ -133,6 +133,15 @@ int cb_clip_encode_image_f32_device(cb_clip *m, int64_t B, const float *nchw_dev
 int cb_clip_encode_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host,
                             int normalize);
 
+/* Pipelined form of cb_clip_encode_image_u8 for the index-time loop
+ * (build-index.py:30-58 re-shaped to batches): submit() queues H2D copy + forward
+ * + D2H copy and returns; the copy of batch i+1 overlaps the forward pass of
+ * batch i (two staging slots).  out_host is valid after cb_clip_sync().  B <=
+ * max_image_batch; host buffers should be pinned and must outlive the sync. */
+int cb_clip_submit_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host,
+                            int normalize);
+int cb_clip_sync(cb_clip *m);
+
 /* text_features = model.encode_text(texts)              query-index.py:108
  * ids: B x 77 int32 tokens as produced by clip.tokenize (query-index.py:107);
  * the EOT position is argmax(ids) per row. out: B x 512 float32. */

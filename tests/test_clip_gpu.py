@@ -234,3 +234,16 @@ def test_full_batch_256_properties(sd):
     assert _cos(torch, out[pick], ref) >= COS_MIN
     small = m.encode_image(imgs[pick].cuda(), normalize=True).cpu()
     assert _cos(torch, small, out[pick]) >= 0.99999
+
+
+def test_pipelined_submit_equals_blocking_call(model, golden_inputs):
+    """cb_clip_submit_image_u8 / cb_clip_sync (copy of batch i+1 overlaps compute of batch i)
+    returns exactly what the blocking entry point returns, for more batches than slots."""
+    import torch
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randint(0, 256, (n, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory()
+               for n in (16, 5, 16, 1, 9)]
+    outs = model.encode_image_batches_host(batches, normalize=True)
+    for b, o in zip(batches, outs):
+        ref = model.encode_image_u8_host(b.numpy(), normalize=True)
+        assert np.array_equal(o.numpy(), ref)
