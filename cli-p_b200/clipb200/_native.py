@@ -67,6 +67,7 @@ SIGNATURES = {
     "cb_preprocess_f32_device": (_int, [_p, _p, _int, _p]),
     "cb_l2norm_f32_device": (_int, [_p, _p, _int, _int, _p]),
     "cb_gemm_f16_device": (_int, [_int, _int, _int, _p, _p, _p, _p, _p, _p, _int, _int, _p]),
+    "cb_flatip_batch_stats": (_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "cb_flatip_timing": (_int, [_p, _int]),
     "cb_flatip_timing_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(_int)]),
 }

@@ -27,6 +27,14 @@
 
 namespace cb {
 
+// tensor-core batch path (flatip_batch.cu)
+struct BatchWs;
+BatchWs *batch_ws_new();
+void batch_ws_delete(BatchWs *w);
+int flatip_search_batch(BatchWs *w, const void *rows_f16, int64_t n, int device, int64_t nq, const float *q_dev,
+                        int64_t k, float *D_dev, int64_t *I_dev, int64_t id_base, cudaStream_t s,
+                        bool *overflowed);
+
 constexpr int kD = 512;
 constexpr int kBins0 = 2048;           // 11 + 11 + 10 bit digits
 constexpr int kMaxNQ = 4;              // queries sharing one pass over the shard (register budget)
@@ -483,6 +491,8 @@ struct cb_index {
     void *h_stage = nullptr;
     int64_t stage_bytes = 0;
     int scan_blocks_per_sm[2][3] = {{0}};
+    cb::BatchWs *bws = nullptr;      // workspace of the tensor-core batch path
+    int64_t n_batch_searches = 0, n_batch_overflows = 0;
     // optional live timing of the scan kernel (bench.py roofline): event pairs on the
     // launching stream, resolved lazily by cb_flatip_timing_read
     bool timing = false;
@@ -631,6 +641,7 @@ void cb_flatip_free(cb_index *ix) {
     cudaFree(ix->rows); cudaFree(ix->scores); cudaFree(ix->ws); cudaFree(ix->cand);
     cudaFree(ix->d_q); cudaFree(ix->d_D); cudaFree(ix->d_I); cudaFree(ix->d_stage);
     cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_D); cudaFreeHost(ix->h_I); cudaFreeHost(ix->h_stage);
+    cb::batch_ws_delete(ix->bws);
     for (int i = 0; i < cb_index::kEv; i++) {
         if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
         if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]);
@@ -727,6 +738,21 @@ int cb_flatip_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_
         CB_LAUNCH_CHECK();
         return CB_OK;
     }
+    // query batches: tensor-core GEMM + fused threshold filter (fp16 shards, k <= 1024).
+    // Below ~16 queries the HBM-bound streaming scan is faster (crossover
+    // where 2 x 256-query MMA work costs more than re-streaming the shard per 4 queries).
+    int64_t batch_min = 16;
+    if (const char *e = getenv("CLIPB200_BATCH_MIN_NQ")) batch_min = atoll(e);
+    if (nq >= batch_min && ix->dtype == CB_F16 && k <= 1024 && ix->ntotal >= 8192) {
+        if (!ix->bws) ix->bws = batch_ws_new();
+        bool overflowed = false;
+        int brc = flatip_search_batch(ix->bws, ix->rows, ix->ntotal, ix->device, nq, q_dev, k, D_dev, I_dev,
+                                      id_base, s, &overflowed);
+        if (brc) return brc;
+        ix->n_batch_searches++;
+        if (!overflowed) return CB_OK;
+        ix->n_batch_overflows++;      // adversarial row order: redo exactly with the scan path
+    }
     int rc = ensure_ws(ix, std::min<int64_t>(k, ix->ntotal));
     if (rc) return rc;
     for (int64_t q0 = 0; q0 < nq; q0 += kMaxNQ) {
@@ -800,6 +826,13 @@ int cb_topk_merge_device(int R, int64_t nq, int64_t k, const float *D_in, const 
                                                                D_out, I_out, g_s, g_i, p2);
     CB_LAUNCH_CHECK();
     if (g_s) { CB_CUDA(cudaFreeAsync(g_s, s)); CB_CUDA(cudaFreeAsync(g_i, s)); }
+    return CB_OK;
+}
+
+int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_overflow_fallbacks) {
+    CB_REQUIRE(ix && n_batch_searches && n_overflow_fallbacks, "cb_flatip_batch_stats: null argument");
+    *n_batch_searches = ix->n_batch_searches;
+    *n_overflow_fallbacks = ix->n_batch_overflows;
     return CB_OK;
 }
 

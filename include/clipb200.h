@@ -76,6 +76,13 @@ int cb_flatip_search(cb_index *ix, int64_t nq, const float *q_host, int64_t k,
 int cb_flatip_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k,
                             float *D_dev, int64_t *I_dev, int64_t id_base, void *stream);
 
+/* search dispatch: nq < 16 (or fp32 storage, or k > 1024) streams the shard once per
+ * 4 queries (HBM-bound scan); larger batches on fp16 shards run the tcgen05 GEMM
+ * with a fused per-query threshold filter (tensor-bound; synchronises the stream
+ * once to read its overflow flag and falls back to the scan path if a candidate
+ * list overflowed).  Counters for tests / benches: */
+int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_overflow_fallbacks);
+
 /* Merge R per-shard results into [nq][k] by (-score, id); ids < 0 are padding.
  * Shard r's block [nq][k] starts at D_in + r*shard_stride_D (elements) and
  * I_in + r*shard_stride_I; a stride <= 0 means densely packed [R][nq][k].  Runs
