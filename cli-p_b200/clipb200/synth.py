@@ -30,3 +30,19 @@ def device_unit_rows(n: int, d: int, seed: int, device, dtype, chunk: int = 1 <<
         x = x / x.norm(dim=1, keepdim=True)
         out[lo:lo + m] = x.to(dtype)
     return out
+
+
+def synthetic_tokens(n: int, seed: int = 0):
+    """[49406, t_1..t_m, 49407, 0...] rows with m in [3,20], t in [1000,40000):
+    stand-in for clip.tokenize output while no BPE vocabulary is available offline."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.zeros((n, 77), dtype=torch.int32)
+    m = torch.randint(3, 21, (n,), generator=g)
+    body = torch.randint(1000, 40000, (n, 20), generator=g, dtype=torch.int32)
+    for i in range(n):
+        k = int(m[i])
+        ids[i, 0] = 49406
+        ids[i, 1:1 + k] = body[i, :k]
+        ids[i, 1 + k] = 49407
+    return ids
