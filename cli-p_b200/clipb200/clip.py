@@ -162,28 +162,36 @@ class CLIPB200:
         return out
 
 
-def _transform(n_px: int = 224):
-    """clip._transform: Resize(n_px, bicubic) on the shorter side, CenterCrop, RGB,
-    ToTensor, Normalize -- on the CPU with PIL, as the reference does."""
+def resize_center_crop(image, n_px: int = 224):
+    """The PIL half of clip._transform: Resize(n_px, bicubic) on the shorter side (torchvision
+    rounding: longer side truncated), CenterCrop(n_px), convert("RGB").  Returns a PIL image;
+    everything after this point (ToTensor, Normalize) is exact per-pixel arithmetic, which the
+    uint8 entry points run on the GPU -- so PIL pixels in == reference transform out."""
     from PIL import Image
+    w, h = image.size
+    if (w, h) != (n_px, n_px):
+        if w <= h:
+            nw, nh = n_px, int(n_px * h / w)
+        else:
+            nw, nh = int(n_px * w / h), n_px
+        image = image.resize((nw, nh), Image.BICUBIC)
+        left, top = int(round((nw - n_px) / 2.0)), int(round((nh - n_px) / 2.0))
+        image = image.crop((left, top, left + n_px, top + n_px))
+    return image.convert("RGB")
 
+
+def image_to_u8(image, n_px: int = 224) -> np.ndarray:
+    """PIL image -> uint8 [n_px, n_px, 3] ready for encode_image's uint8 path."""
+    return np.array(resize_center_crop(image, n_px), dtype=np.uint8)
+
+
+def _transform(n_px: int = 224):
+    """clip._transform on the CPU, as the reference does (build-index.py:48)."""
     mean = torch.tensor(_MEAN).view(3, 1, 1)
     std = torch.tensor(_STD).view(3, 1, 1)
 
     def transform(image):
-        w, h = image.size
-        if (w, h) != (n_px, n_px):
-            # torchvision Resize(int): shorter side -> n_px, longer side truncated;
-            # CenterCrop rounds half the margin
-            if w <= h:
-                nw, nh = n_px, int(n_px * h / w)
-            else:
-                nw, nh = int(n_px * w / h), n_px
-            image = image.resize((nw, nh), Image.BICUBIC)
-            left, top = int(round((nw - n_px) / 2.0)), int(round((nh - n_px) / 2.0))
-            image = image.crop((left, top, left + n_px, top + n_px))
-        image = image.convert("RGB")
-        x = torch.from_numpy(np.asarray(image, dtype=np.uint8).copy()).permute(2, 0, 1).float().div(255.0)
+        x = torch.from_numpy(image_to_u8(image, n_px).copy()).permute(2, 0, 1).float().div(255.0)
         return (x - mean) / std
 
     return transform

@@ -1,0 +1,100 @@
+"""GPU, BASELINE configs[0] in miniature: synthetic JPEG/PNG folder -> batched build-index
+pipeline (PIL decode/resize on the CPU, ToTensor/Normalize + ViT-B/32 + L2-norm on the GPU,
+LMDB-format store, flat index) -> text query top-20, against the CPU oracle pipeline."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_folder(root, n=150):
+    from PIL import Image
+    rng = np.random.default_rng(1234)
+    os.makedirs(root, exist_ok=True)
+    sizes = [(224, 224), (224, 224), (320, 240), (200, 300), (640, 480)]
+    for i in range(n):
+        w, h = sizes[i % len(sizes)]
+        base = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+        im = Image.fromarray(base).resize((w, h), Image.BICUBIC)
+        arr = np.clip(np.asarray(im, dtype=np.float32) + rng.normal(0, 8, (h, w, 3)), 0, 255).astype(np.uint8)
+        ext = ".png" if i % 10 == 0 else (".JPG" if i % 7 == 0 else ".jpg")
+        Image.fromarray(arr).save(os.path.join(root, f"img_{i:06d}{ext}"), quality=90)
+    open(os.path.join(root, "broken.jpg"), "wb").write(b"not a jpeg at all")
+    open(os.path.join(root, "notes.txt"), "w").write("ignored")
+
+
+def test_build_index_and_query_against_oracle(tmp_path, monkeypatch):
+    import torch
+    from PIL import Image
+    from clipb200 import clip, faiss, indexer, lmdb, weights
+    from oracle import clip_ref, flatip_ref
+
+    folder = str(tmp_path / "photos") + "/"
+    _make_folder(folder)
+    monkeypatch.chdir(tmp_path)
+    sd = weights.synthetic_state_dict(0)
+    model = clip.CLIPB200(sd, device=0, max_image_batch=64, max_text_batch=4)
+    env = lmdb.open("vectors.lmdb", map_size=1 << 30, max_dbs=4)
+    log = io.StringIO()
+    ok, bad = indexer.embed_folders([folder], env, model, batch=64, out=log)
+    assert (ok, bad) == (150, 1)
+    text = log.getvalue()
+    assert text.startswith(f"CLIPing {folder}...") and text.count(".") >= 150 and text.count("#") == 1
+
+    # resume: nothing new the second time (build-index.py:42-44)
+    log2 = io.StringIO()
+    assert indexer.embed_folders([folder], env, model, batch=64, out=log2) == (0, 1)
+
+    index = indexer.build_index(env, faiss, index_path="images.index", out=io.StringIO())
+    assert index.ntotal == 150 and os.path.exists("images.index")
+
+    # stored vectors vs the fp32 oracle run on the reference's own CPU transform
+    fn_db, idx_db = env.open_db(b"fn_db"), env.open_db(b"idx_db")
+    transform = clip._transform(224)
+    with env.begin(db=fn_db) as txn:
+        keys = [k for k, _ in txn.cursor()]
+        assert keys == sorted(keys) and len(keys) == 150
+        sample = keys[::17]
+        x = torch.stack([transform(Image.open(k.decode())) for k in sample])
+        ref = clip_ref.l2_normalize_rows(clip_ref.encode_image(sd, x)).numpy()
+        got = np.stack([np.frombuffer(txn.get(k), dtype=np.float32) for k in sample])
+        assert all(len(txn.get(k)) == 2048 for k in sample)
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() >= 0.999, cos.min()
+    with env.begin(db=idx_db) as txn:
+        assert txn.get(b"0") == keys[0] and txn.get(b"149") == keys[149]
+
+    # text query, top-20 (c 20 -> search(k=21), rank 0 skipped: query-index.py:111-116)
+    searcher = indexer.Searcher(env, index, model)
+    tokens = clip_ref.synthetic_tokens(1, seed=4)
+    feats = searcher.features_for_tokens(tokens)
+    rows = searcher.results(feats, k=20, offset=0)
+    assert len(rows) == 20
+    with env.begin(db=fn_db) as txn:
+        all_vecs = np.stack([np.frombuffer(txn.get(k), dtype=np.float32) for k in keys])
+    Dref, Iref = flatip_ref.search(feats, all_vecs, 21)
+    Dgot = np.array([[r[0] for r in rows]], dtype=np.float32)
+    Igot = np.array([[r[1] for r in rows]])
+    okk, _, msg = flatip_ref.ids_match_with_tolerance(Dref[:, 1:], Iref[:, 1:], Dgot, Igot)
+    assert okk, msg
+    assert rows[0][2] == keys[rows[0][1]].decode()
+    assert indexer.Searcher.format_row(rows[0]).split(" ")[0] == f"{rows[0][0]:.4f}"
+    # the text feature itself agrees with the oracle text tower
+    tref = clip_ref.l2_normalize_rows(clip_ref.encode_text(sd, tokens)).numpy()
+    assert float((feats * tref).sum()) >= 0.999
+
+    # `i ID`: the stored vector's best match is itself (rank 0, skipped by the REPL)
+    f7 = searcher.features_for_id(7)
+    D, I = index.search(f7, 3)
+    assert I[0][0] == 7 and abs(D[0][0] - 1.0) < 1e-3
+    env.close()
+
+    # reopen from disk like query-index.py:25-29
+    env2 = lmdb.open("vectors.lmdb", map_size=1 << 30, max_dbs=4)
+    index2 = faiss.read_index("images.index")
+    s2 = indexer.Searcher(env2, index2, model)
+    assert s2.results(feats, k=20, offset=0) == rows
+    env2.close()
