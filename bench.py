@@ -118,11 +118,14 @@ def dist_env():
     return rank, world, local
 
 
-def timed_region(torch, dist, world, fn, steps, warmup, sampler=None):
+def timed_region(torch, dist, world, fn, steps, warmup, sampler=None, drain=None):
     """W untimed steps, then exactly K steps between barrier+sync, CUDA events on the
-    current stream, MAX over ranks.  Returns seconds."""
+    current stream, MAX over ranks.  Returns seconds.  `drain` (optional) orders the current
+    stream after work the steps queued on other streams; it runs before the end event."""
     for _ in range(warmup):
         fn()
+    if drain:
+        drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -133,6 +136,8 @@ def timed_region(torch, dist, world, fn, steps, warmup, sampler=None):
     e0.record()
     for _ in range(steps):
         fn()
+    if drain:
+        drain()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:

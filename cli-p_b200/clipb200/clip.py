@@ -303,11 +303,23 @@ def bench_hooks():
         L = N.lib()
         it = {"i": 0}
 
-        def step_dev():
+        outs_dev = [torch.empty((B, 512), dtype=torch.float32, device=dev) for _ in range(2)]
+
+        def step_one_lane():
             im = imgs[it["i"] % nb]
             it["i"] += 1
             N.check(L.cb_clip_encode_image_u8_device(model.handle, B, C.c_void_p(im.data_ptr()),
                                                      C.c_void_p(out.data_ptr()), 1, model._stream()))
+
+        def step_dev():
+            # throughput mode: two batches in flight on the model's two lanes, device-resident input
+            j = it["i"]
+            it["i"] += 1
+            N.check(L.cb_clip_submit_image_u8_device(model.handle, B, C.c_void_p(imgs[j % nb].data_ptr()),
+                                                     C.c_void_p(outs_dev[j % 2].data_ptr()), 1, model._stream()))
+
+        def join_dev():
+            N.check(L.cb_clip_join(model.handle, model._stream()))
 
         out_pinned = [torch.empty((B, 512), dtype=torch.float32).pin_memory() for _ in range(nb)]
 
@@ -322,17 +334,27 @@ def bench_hooks():
         def e2e_sync():
             N.check(L.cb_clip_sync(model.handle))
 
+        # (1) kernel quality: one batch in flight, every GEMM launch bracketed by CUDA events
         for _ in range(args.warmup):
-            step_dev()
+            step_one_lane()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if rank == 0 else None
-        L.cb_clip_timing(model.handle, 1)
-        N.launch_count(reset=True)
-        secs = timed_region(torch, dist, world, step_dev, args.steps, 0, sampler)
-        launches = N.launch_count()
+        L.cb_clip_timing(model.handle, 2 if os.environ.get("CLIPB200_BREAKDOWN") else 1)
+        one_lane_steps = max(3, args.steps // 2)
+        one_lane_secs = timed_region(torch, dist, world, step_one_lane, one_lane_steps, 0)
         ms, fl, cnt = C.c_double(0), C.c_double(0), C.c_int(0)
+        br = (C.c_double * 4)()
+        L.cb_clip_timing_breakdown(model.handle, br)
         L.cb_clip_timing_read(model.handle, C.byref(ms), C.byref(fl), C.byref(cnt))
         L.cb_clip_timing(model.handle, 0)
+        # (2) the reported value: exactly K steps, two lanes in flight
+        sampler = ClockSampler(local) if rank == 0 else None
+        for _ in range(args.warmup):
+            step_dev()
+        join_dev()
+        torch.cuda.synchronize()
+        N.launch_count(reset=True)
+        secs = timed_region(torch, dist, world, step_dev, args.steps, 0, sampler, drain=join_dev)
+        launches = N.launch_count()
         clocks = sampler.stop() if sampler else None
         e2e_secs = timed_region_wall(torch, dist, world, step_e2e, args.steps, args.warmup, drain=e2e_sync)
         peaks = load_peaks()
@@ -343,6 +365,8 @@ def bench_hooks():
             "dtype": "f16 (fp32 accumulate, fp32 LayerNorm statistics)",
             "config": {"workload": "ViT-B/32 encode_image on synthetic 224px uint8 images, batch 256 per GPU, "
                                    "data-parallel, preprocess + forward + L2-normalise (BASELINE configs[1])",
+                       "in_flight": "two batches per GPU (two lanes: the HBM-bound kernels of one batch overlap the "
+                                    "GEMMs of the other); a step is one batch",
                        "batch_per_gpu": B, "image": "224x224x3 uint8",
                        "l2": "working set per step (weights 176 MB + activations ~290 MB + 4 rotating input "
                              "batches of 38.5 MB) exceeds the 126 MB L2"},
@@ -351,12 +375,19 @@ def bench_hooks():
             "gpu_launches": int(launches),
             "step_tflops_per_gpu": B * args.steps * GFLOP / 1e3 / secs,
         }
+        if os.environ.get("CLIPB200_BREAKDOWN"):
+            res["breakdown_ms_per_step"] = {k: br[i] / one_lane_steps for i, k in
+                                            enumerate(("gemm", "attention", "layernorm", "other"))}
         if cnt.value:
             ach = fl.value / (ms.value / 1e3) / 1e12
             res["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
                                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
                                "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step)",
-                               "kernel_ms": ms.value / cnt.value, "gemm_share_of_step": ms.value / 1e3 / secs,
+                               "kernel_ms": ms.value / cnt.value,
+                               "gemm_share_of_step": ms.value / 1e3 / one_lane_secs,
+                               "measured": f"{one_lane_steps} steps with one batch in flight "
+                                           f"({one_lane_secs / one_lane_steps * 1e3:.3f} ms/step); the reported value "
+                                           "keeps two batches in flight",
                                "peak_source": peaks["source"] + " (cuBLAS bf16 sustained; burst "
                                               f"{peaks['bf16_tflops']:.0f})"}
         return res, clocks

@@ -51,14 +51,19 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
     const int W = heads * HD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // stage q|k|v of this head: 3 x LP rows x 8 chunks of 16 B; rows >= L are zero
+    // stage q|k|v of this head: 3 x LP rows x 8 chunks of 16 B, global -> shared with cp.async
+    // (no register round trip); rows >= L are zero
     for (int i = threadIdx.x; i < 3 * LP * 8; i += blockDim.x) {
         const int ch = i & 7, row = (i >> 3) % LP, mat = i / (8 * LP);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row < L) v = *reinterpret_cast<const uint4 *>(qkv + ((size_t)(b * L + row) * 3 + mat) * W + h * HD + ch * 8);
         __half *dst = (mat == 0 ? sQ : (mat == 1 ? sK : sV)) + row * LDS + ch * 8;
-        *reinterpret_cast<uint4 *>(dst) = v;
+        if (row < L) {
+            const __half *src = qkv + ((size_t)(b * L + row) * 3 + mat) * W + h * HD + ch * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        } else {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+        }
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // Q fragments of this warp's 16 rows

@@ -41,6 +41,24 @@ struct LayerW {
 
 constexpr int VW = 768, VL = 50, VH = 12, TW = 512, TL = 77, TH = 8, LAYERS = 12, ED = 512, VOCAB = 49408;
 
+// activation workspace of one forward pass in flight
+struct Ws {
+    __half *patches = nullptr, *x = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr;
+    float *emb = nullptr;
+    int *eot = nullptr;
+};
+
+// a lane = workspace + streams + staging for the pipelined submit API; two lanes run
+// concurrently so the memory-bound kernels of one batch overlap the GEMMs of the other
+struct Lane {
+    Ws ws;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    uint8_t *img = nullptr;
+    float *out = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool used = false;
+};
+
 }  // namespace
 
 struct cb_clip {
@@ -53,25 +71,21 @@ struct cb_clip {
     const float *vpos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
     const float *tok_emb = nullptr, *tpos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
     float *cls_pos = nullptr;     // class_embedding + positional_embedding[0]
-    // workspace
-    __half *patches = nullptr, *x = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr;
-    float *emb = nullptr;
-    int *eot = nullptr;
+    Ws ws;                        // workspace of the caller-stream (_device) entry points
     // staging for the host-pointer entry points
     uint8_t *d_img = nullptr;
     int32_t *d_ids = nullptr;
     float *d_out = nullptr;
     cudaStream_t stream = nullptr;
-    // pipelined host entry point: two input/output staging slots, copies on their own stream
-    cudaStream_t copy_stream = nullptr;
-    uint8_t *slot_img[2] = {nullptr, nullptr};
-    float *slot_out[2] = {nullptr, nullptr};
-    cudaEvent_t slot_copied[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
-    bool slot_used[2] = {false, false};
-    int next_slot = 0;
+    // pipelined submit API: two lanes in flight
+    Lane lanes[2];
+    bool lanes_ready = false;
+    int next_lane = 0;
+    cudaEvent_t fence_ev = nullptr;
     // live GEMM timing (bench.py roofline)
-    bool timing = false;
+    int timing = 0;                 // 0 off, 1 GEMM launches only, 2 every kernel class
     std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_cat;        // category of each event pair: 0 gemm, 1 attention, 2 layernorm, 3 other
     int ev_n = 0;
     double gemm_flops = 0;
 };
@@ -141,8 +155,24 @@ int timed_gemm(cb_clip *m, const GemmArgs &g, cudaStream_t s) {
     if (rc) return rc;
     if (t) {
         CB_CUDA(cudaEventRecord(m->ev[m->ev_n + 1], s));
+        m->ev_cat[m->ev_n / 2] = 0;
         m->ev_n += 2;
         m->gemm_flops += 2.0 * g.M * g.N * g.K;
+    }
+    return CB_OK;
+}
+
+// bracket a non-GEMM launch with events when the full breakdown is requested
+template <typename F>
+int timed_other(cb_clip *m, int cat, cudaStream_t s, F &&launch) {
+    const bool t = m->timing >= 2 && m->ev_n + 2 <= (int)m->ev.size();
+    if (t) CB_CUDA(cudaEventRecord(m->ev[m->ev_n], s));
+    int rc = launch();
+    if (rc) return rc;
+    if (t) {
+        CB_CUDA(cudaEventRecord(m->ev[m->ev_n + 1], s));
+        m->ev_cat[m->ev_n / 2] = cat;
+        m->ev_n += 2;
     }
     return CB_OK;
 }
@@ -155,45 +185,72 @@ GemmArgs mk(const __half *A, const __half *W, const float *bias, const __half *r
 }
 
 // 12 residual attention blocks over x [B*L, W] (in place)
-int run_blocks(cb_clip *m, const LayerW *lw, int W, int heads, int B, int L, bool causal, cudaStream_t s) {
+int run_blocks(cb_clip *m, Ws &w, const LayerW *lw, int W, int heads, int B, int L, bool causal, cudaStream_t s) {
     const int rows = B * L;
     for (int i = 0; i < LAYERS; i++) {
         int rc;
-        if ((rc = layernorm_f16(m->x, m->h, lw[i].ln1_g, lw[i].ln1_b, rows, W, 1, nullptr, nullptr, 0, s))) return rc;
-        if ((rc = timed_gemm(m, mk(m->h, lw[i].w_qkv, lw[i].b_qkv, nullptr, m->qkv, rows, 3 * W, W, EPI_BIAS), s))) return rc;
-        if ((rc = attention_f16(m->qkv, m->att, B, L, heads, causal, s))) return rc;
-        if ((rc = timed_gemm(m, mk(m->att, lw[i].w_o, lw[i].b_o, m->x, m->x, rows, W, W, EPI_BIAS_RESID), s))) return rc;
-        if ((rc = layernorm_f16(m->x, m->h, lw[i].ln2_g, lw[i].ln2_b, rows, W, 1, nullptr, nullptr, 0, s))) return rc;
-        if ((rc = timed_gemm(m, mk(m->h, lw[i].w_fc, lw[i].b_fc, nullptr, m->mlp, rows, 4 * W, W, EPI_BIAS_GELU), s))) return rc;
-        if ((rc = timed_gemm(m, mk(m->mlp, lw[i].w_proj, lw[i].b_proj, m->x, m->x, rows, W, 4 * W, EPI_BIAS_RESID), s))) return rc;
+        if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.h, lw[i].ln1_g, lw[i].ln1_b, rows, W, 1, nullptr, nullptr, 0, s); }))) return rc;
+        if ((rc = timed_gemm(m, mk(w.h, lw[i].w_qkv, lw[i].b_qkv, nullptr, w.qkv, rows, 3 * W, W, EPI_BIAS), s))) return rc;
+        if ((rc = timed_other(m, 1, s, [&] { return attention_f16(w.qkv, w.att, B, L, heads, causal, s); }))) return rc;
+        if ((rc = timed_gemm(m, mk(w.att, lw[i].w_o, lw[i].b_o, w.x, w.x, rows, W, W, EPI_BIAS_RESID), s))) return rc;
+        if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.h, lw[i].ln2_g, lw[i].ln2_b, rows, W, 1, nullptr, nullptr, 0, s); }))) return rc;
+        if ((rc = timed_gemm(m, mk(w.h, lw[i].w_fc, lw[i].b_fc, nullptr, w.mlp, rows, 4 * W, W, EPI_BIAS_GELU), s))) return rc;
+        if ((rc = timed_gemm(m, mk(w.mlp, lw[i].w_proj, lw[i].b_proj, w.x, w.x, rows, W, 4 * W, EPI_BIAS_RESID), s))) return rc;
     }
     return CB_OK;
 }
 
-// patches (already in m->patches) -> out [B,512] fp32
-int vision_from_patches(cb_clip *m, int B, float *out_dev, int normalize, cudaStream_t s) {
+cudaError_t alloc_ws(const cb_clip *m, Ws &w) {
+    // the larger of the two towers, element counts
+    const size_t rows_v = (size_t)m->max_img * VL, rows_t = (size_t)m->max_txt * TL;
+    const size_t n_x = std::max(rows_v * VW, rows_t * TW);
+    const size_t n_cls = std::max((size_t)m->max_img * VW, (size_t)m->max_txt * TW);
+    const size_t nb = std::max(m->max_img, m->max_txt);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 256)); };
+    A((void **)&w.patches, (size_t)m->max_img * 49 * 3072 * 2);
+    A((void **)&w.x, n_x * 2); A((void **)&w.h, n_x * 2); A((void **)&w.att, n_x * 2);
+    A((void **)&w.qkv, 3 * n_x * 2); A((void **)&w.mlp, 4 * n_x * 2);
+    A((void **)&w.cls, n_cls * 2); A((void **)&w.emb, nb * ED * 4); A((void **)&w.eot, nb * 4);
+    return e;
+}
+
+void free_ws(Ws &w) {
+    void *bufs[] = {w.patches, w.x, w.h, w.qkv, w.att, w.mlp, w.cls, w.emb, w.eot};
+    for (void *p : bufs) cudaFree(p);
+    w = Ws();
+}
+
+// patches (already in w.patches) -> out [B,512] fp32
+int vision_from_patches(cb_clip *m, Ws &w, int B, float *out_dev, int normalize, cudaStream_t s) {
     int rc;
-    GemmArgs g = mk(m->patches, m->conv1_w, nullptr, nullptr, m->x, B * 49, VW, 3072, EPI_PATCH);
+    GemmArgs g = mk(w.patches, m->conv1_w, nullptr, nullptr, w.x, B * 49, VW, 3072, EPI_PATCH);
     g.pos = m->vpos;
     if ((rc = timed_gemm(m, g, s))) return rc;
     // ln_pre in place; class-token rows (row % 50 == 0) come from class_embedding + pos[0]
-    if ((rc = layernorm_f16(m->x, m->x, m->ln_pre_g, m->ln_pre_b, B * VL, VW, 1, nullptr, m->cls_pos, VL, s))) return rc;
-    if ((rc = run_blocks(m, m->vis, VW, VH, B, VL, false, s))) return rc;
-    if ((rc = layernorm_f16(m->x, m->cls, m->ln_post_g, m->ln_post_b, B, VW, VL, nullptr, nullptr, 0, s))) return rc;
-    float *emb = normalize ? m->emb : out_dev;
-    if ((rc = timed_gemm(m, mk(m->cls, m->vproj_w, nullptr, nullptr, emb, B, ED, VW, EPI_F32), s))) return rc;
+    if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.x, m->ln_pre_g, m->ln_pre_b, B * VL, VW, 1, nullptr, m->cls_pos, VL, s); }))) return rc;
+    if ((rc = run_blocks(m, w, m->vis, VW, VH, B, VL, false, s))) return rc;
+    if ((rc = layernorm_f16(w.x, w.cls, m->ln_post_g, m->ln_post_b, B, VW, VL, nullptr, nullptr, 0, s))) return rc;
+    float *emb = normalize ? w.emb : out_dev;
+    if ((rc = timed_gemm(m, mk(w.cls, m->vproj_w, nullptr, nullptr, emb, B, ED, VW, EPI_F32), s))) return rc;
     if (normalize && (rc = l2norm_rows_f32(emb, out_dev, B, ED, s))) return rc;
     return CB_OK;
 }
 
-int text_forward(cb_clip *m, int B, const int32_t *ids_dev, float *out_dev, int normalize, cudaStream_t s) {
+int encode_u8_chunk(cb_clip *m, Ws &w, int b, const uint8_t *hwc_dev, float *out_dev, int normalize, cudaStream_t s) {
+    int rc = timed_other(m, 3, s, [&] { return preprocess_u8(hwc_dev, w.patches, b, s); });
+    if (rc) return rc;
+    return vision_from_patches(m, w, b, out_dev, normalize, s);
+}
+
+int text_forward(cb_clip *m, Ws &w, int B, const int32_t *ids_dev, float *out_dev, int normalize, cudaStream_t s) {
     int rc;
-    if ((rc = text_embed(ids_dev, m->tok_emb, m->tpos, m->x, m->eot, B, TL, TW, VOCAB, s))) return rc;
-    if ((rc = run_blocks(m, m->txt, TW, TH, B, TL, true, s))) return rc;
+    if ((rc = text_embed(ids_dev, m->tok_emb, m->tpos, w.x, w.eot, B, TL, TW, VOCAB, s))) return rc;
+    if ((rc = run_blocks(m, w, m->txt, TW, TH, B, TL, true, s))) return rc;
     // ln_final only on the EOT rows (LayerNorm is per-row, so gathering first is exact)
-    if ((rc = layernorm_f16(m->x, m->cls, m->lnf_g, m->lnf_b, B, TW, 1, m->eot, nullptr, 0, s))) return rc;
-    float *emb = normalize ? m->emb : out_dev;
-    if ((rc = timed_gemm(m, mk(m->cls, m->tproj_w, nullptr, nullptr, emb, B, ED, TW, EPI_F32), s))) return rc;
+    if ((rc = layernorm_f16(w.x, w.cls, m->lnf_g, m->lnf_b, B, TW, 1, w.eot, nullptr, 0, s))) return rc;
+    float *emb = normalize ? w.emb : out_dev;
+    if ((rc = timed_gemm(m, mk(w.cls, m->tproj_w, nullptr, nullptr, emb, B, ED, TW, EPI_F32), s))) return rc;
     if (normalize && (rc = l2norm_rows_f32(emb, out_dev, B, ED, s))) return rc;
     return CB_OK;
 }
@@ -220,18 +277,9 @@ int cb_clip_create(int device, int max_image_batch, int max_text_batch, cb_clip 
     m->device = device;
     m->max_img = max_image_batch;
     m->max_txt = max_text_batch;
-    // workspace: the larger of the two towers, element counts
-    const size_t rows_v = (size_t)max_image_batch * VL, rows_t = (size_t)max_text_batch * TL;
-    const size_t n_x = std::max(rows_v * VW, rows_t * TW);
-    const size_t n_qkv = 3 * n_x, n_mlp = 4 * n_x;
-    const size_t n_cls = std::max((size_t)max_image_batch * VW, (size_t)max_text_batch * TW);
     const size_t nb = std::max(max_image_batch, max_text_batch);
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = alloc_ws(m, m->ws);
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 256)); };
-    A((void **)&m->patches, (size_t)max_image_batch * 49 * 3072 * 2);
-    A((void **)&m->x, n_x * 2); A((void **)&m->h, n_x * 2); A((void **)&m->att, n_x * 2);
-    A((void **)&m->qkv, n_qkv * 2); A((void **)&m->mlp, n_mlp * 2);
-    A((void **)&m->cls, n_cls * 2); A((void **)&m->emb, nb * ED * 4); A((void **)&m->eot, nb * 4);
     A((void **)&m->d_img, (size_t)max_image_batch * 224 * 224 * 3);
     A((void **)&m->d_ids, (size_t)max_text_batch * TL * 4);
     A((void **)&m->d_out, nb * ED * 4);
@@ -251,15 +299,20 @@ void cb_clip_free(cb_clip *m) {
     DeviceGuard g(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (auto &kv : m->params) cudaFree(kv.second.dev);
-    void *bufs[] = {m->patches, m->x, m->h, m->qkv, m->att, m->mlp, m->cls, m->emb, m->eot, m->d_img, m->d_ids, m->d_out, m->cls_pos};
+    free_ws(m->ws);
+    void *bufs[] = {m->d_img, m->d_ids, m->d_out, m->cls_pos};
     for (void *p : bufs) cudaFree(p);
     for (cudaEvent_t ev : m->ev) cudaEventDestroy(ev);
-    for (int i = 0; i < 2; i++) {
-        cudaFree(m->slot_img[i]); cudaFree(m->slot_out[i]);
-        if (m->slot_copied[i]) cudaEventDestroy(m->slot_copied[i]);
-        if (m->slot_done[i]) cudaEventDestroy(m->slot_done[i]);
+    for (Lane &l : m->lanes) {
+        if (l.stream) cudaStreamSynchronize(l.stream);
+        free_ws(l.ws);
+        cudaFree(l.img); cudaFree(l.out);
+        if (l.copied) cudaEventDestroy(l.copied);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.copy_stream) cudaStreamDestroy(l.copy_stream);
+        if (l.stream) cudaStreamDestroy(l.stream);
     }
-    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->fence_ev) cudaEventDestroy(m->fence_ev);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -339,9 +392,8 @@ int cb_clip_encode_image_u8_device(cb_clip *m, int64_t B, const uint8_t *hwc_dev
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t lo = 0; lo < B; lo += m->max_img) {
         const int b = (int)std::min<int64_t>(m->max_img, B - lo);
-        int rc = preprocess_u8(hwc_dev + (size_t)lo * 224 * 224 * 3, m->patches, b, s);
+        int rc = encode_u8_chunk(m, m->ws, b, hwc_dev + (size_t)lo * 224 * 224 * 3, out_dev + lo * ED, normalize, s);
         if (rc) return rc;
-        if ((rc = vision_from_patches(m, b, out_dev + lo * ED, normalize, s))) return rc;
     }
     return CB_OK;
 }
@@ -357,9 +409,9 @@ int cb_clip_encode_image_f32_device(cb_clip *m, int64_t B, const float *nchw_dev
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t lo = 0; lo < B; lo += m->max_img) {
         const int b = (int)std::min<int64_t>(m->max_img, B - lo);
-        int rc = preprocess_f32(nchw_dev + (size_t)lo * 3 * 224 * 224, m->patches, b, s);
+        int rc = preprocess_f32(nchw_dev + (size_t)lo * 3 * 224 * 224, m->ws.patches, b, s);
         if (rc) return rc;
-        if ((rc = vision_from_patches(m, b, out_dev + lo * ED, normalize, s))) return rc;
+        if ((rc = vision_from_patches(m, m->ws, b, out_dev + lo * ED, normalize, s))) return rc;
     }
     return CB_OK;
 }
@@ -375,7 +427,7 @@ int cb_clip_encode_text_device(cb_clip *m, int64_t B, const int32_t *ids_dev, fl
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t lo = 0; lo < B; lo += m->max_txt) {
         const int b = (int)std::min<int64_t>(m->max_txt, B - lo);
-        int rc = text_forward(m, b, ids_dev + lo * TL, out_dev + lo * ED, normalize, s);
+        int rc = text_forward(m, m->ws, b, ids_dev + lo * TL, out_dev + lo * ED, normalize, s);
         if (rc) return rc;
     }
     return CB_OK;
@@ -401,44 +453,86 @@ int cb_clip_encode_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, floa
     return CB_OK;
 }
 
-// Pipelined variant of cb_clip_encode_image_u8: returns as soon as the work is queued.  The
-// H2D copy of this batch runs on a copy stream and overlaps the forward pass of the previous
-// batch; results land in out_host after cb_clip_sync().  At most two batches are in flight
-// (two staging slots); host_in/out_host must stay valid (and should be pinned) until then.
+// Pipelined variants: return as soon as the work is queued.  Batches alternate between two
+// lanes (own workspace + streams): the H2D copy of one batch overlaps the forward pass of the
+// other, and the HBM-bound kernels of one forward pass (LayerNorm, attention) overlap the
+// tensor-bound GEMMs of the other.  Results are complete after cb_clip_sync() (host
+// variant) / cb_clip_join() (device variant).  Host buffers should be pinned and must stay
+// valid until then.
+static int lanes_init(cb_clip *m) {
+    if (m->lanes_ready) return CB_OK;
+    const size_t img_bytes = 224 * 224 * 3;
+    for (Lane &l : m->lanes) {
+        cudaError_t e = alloc_ws(m, l.ws);
+        if (e != cudaSuccess) { set_error("lane workspace: %s", cudaGetErrorString(e)); return CB_ERR_OOM; }
+        CB_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CB_CUDA(cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking));
+        CB_CUDA(cudaMalloc(&l.img, (size_t)std::max(m->max_img, 1) * img_bytes));
+        CB_CUDA(cudaMalloc(&l.out, (size_t)std::max(m->max_img, 1) * ED * 4));
+        CB_CUDA(cudaEventCreateWithFlags(&l.copied, cudaEventDisableTiming));
+        CB_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    }
+    CB_CUDA(cudaEventCreateWithFlags(&m->fence_ev, cudaEventDisableTiming));
+    m->lanes_ready = true;
+    return CB_OK;
+}
+
 int cb_clip_submit_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host, int normalize) {
     CLIP_READY(m, "cb_clip_submit_image_u8");
     CB_REQUIRE(B > 0 && B <= m->max_img, "cb_clip_submit_image_u8: B must be in [1, max_image_batch]");
     CB_REQUIRE(hwc_host && out_host, "cb_clip_submit_image_u8: null buffer");
     DeviceGuard g(m->device);
-    const size_t img_bytes = 224 * 224 * 3;
-    if (!m->copy_stream) {
-        CB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            CB_CUDA(cudaMalloc(&m->slot_img[i], (size_t)m->max_img * img_bytes));
-            CB_CUDA(cudaMalloc(&m->slot_out[i], (size_t)m->max_img * ED * 4));
-            CB_CUDA(cudaEventCreateWithFlags(&m->slot_copied[i], cudaEventDisableTiming));
-            CB_CUDA(cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming));
-        }
-    }
-    const int sl = m->next_slot;
-    m->next_slot ^= 1;
-    // the slot's previous forward pass must have consumed its input before we overwrite it
-    if (m->slot_used[sl]) CB_CUDA(cudaStreamWaitEvent(m->copy_stream, m->slot_done[sl], 0));
-    CB_CUDA(cudaMemcpyAsync(m->slot_img[sl], hwc_host, (size_t)B * img_bytes, cudaMemcpyHostToDevice, m->copy_stream));
-    CB_CUDA(cudaEventRecord(m->slot_copied[sl], m->copy_stream));
-    CB_CUDA(cudaStreamWaitEvent(m->stream, m->slot_copied[sl], 0));
-    int rc = cb_clip_encode_image_u8_device(m, B, m->slot_img[sl], m->slot_out[sl], normalize, m->stream);
+    int rc = lanes_init(m);
     if (rc) return rc;
-    CB_CUDA(cudaMemcpyAsync(out_host, m->slot_out[sl], (size_t)B * ED * 4, cudaMemcpyDeviceToHost, m->stream));
-    CB_CUDA(cudaEventRecord(m->slot_done[sl], m->stream));
-    m->slot_used[sl] = true;
+    Lane &l = m->lanes[m->next_lane];
+    m->next_lane ^= 1;
+    // this lane's previous forward pass must have consumed its input before we overwrite it
+    if (l.used) CB_CUDA(cudaStreamWaitEvent(l.copy_stream, l.done, 0));
+    CB_CUDA(cudaMemcpyAsync(l.img, hwc_host, (size_t)B * 224 * 224 * 3, cudaMemcpyHostToDevice, l.copy_stream));
+    CB_CUDA(cudaEventRecord(l.copied, l.copy_stream));
+    CB_CUDA(cudaStreamWaitEvent(l.stream, l.copied, 0));
+    if ((rc = encode_u8_chunk(m, l.ws, (int)B, l.img, l.out, normalize, l.stream))) return rc;
+    CB_CUDA(cudaMemcpyAsync(out_host, l.out, (size_t)B * ED * 4, cudaMemcpyDeviceToHost, l.stream));
+    CB_CUDA(cudaEventRecord(l.done, l.stream));
+    l.used = true;
+    return CB_OK;
+}
+
+// device-resident input and output; ordered after everything queued on `after_stream` so far
+int cb_clip_submit_image_u8_device(cb_clip *m, int64_t B, const uint8_t *hwc_dev, float *out_dev, int normalize,
+                                   void *after_stream) {
+    CLIP_READY(m, "cb_clip_submit_image_u8_device");
+    CB_REQUIRE(B > 0 && B <= m->max_img, "cb_clip_submit_image_u8_device: B must be in [1, max_image_batch]");
+    CB_REQUIRE(hwc_dev && out_dev, "cb_clip_submit_image_u8_device: null buffer");
+    DeviceGuard g(m->device);
+    int rc = lanes_init(m);
+    if (rc) return rc;
+    Lane &l = m->lanes[m->next_lane];
+    m->next_lane ^= 1;
+    CB_CUDA(cudaEventRecord(m->fence_ev, (cudaStream_t)after_stream));
+    CB_CUDA(cudaStreamWaitEvent(l.stream, m->fence_ev, 0));
+    if ((rc = encode_u8_chunk(m, l.ws, (int)B, hwc_dev, out_dev, normalize, l.stream))) return rc;
+    CB_CUDA(cudaEventRecord(l.done, l.stream));
+    l.used = true;
+    return CB_OK;
+}
+
+// make `stream` wait for everything submitted so far (no host synchronisation)
+int cb_clip_join(cb_clip *m, void *stream) {
+    CB_REQUIRE(m != nullptr, "cb_clip_join: null handle");
+    DeviceGuard g(m->device);
+    for (Lane &l : m->lanes)
+        if (l.used) CB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, l.done, 0));
     return CB_OK;
 }
 
 int cb_clip_sync(cb_clip *m) {
     CB_REQUIRE(m != nullptr, "cb_clip_sync: null handle");
     DeviceGuard g(m->device);
-    if (m->copy_stream) CB_CUDA(cudaStreamSynchronize(m->copy_stream));
+    for (Lane &l : m->lanes) {
+        if (l.copy_stream) CB_CUDA(cudaStreamSynchronize(l.copy_stream));
+        if (l.stream) CB_CUDA(cudaStreamSynchronize(l.stream));
+    }
     CB_CUDA(cudaStreamSynchronize(m->stream));
     return CB_OK;
 }
@@ -464,12 +558,26 @@ int cb_clip_encode_text(cb_clip *m, int64_t B, const int32_t *ids_host, float *o
 int cb_clip_timing(cb_clip *m, int enable) {
     CB_REQUIRE(m != nullptr, "cb_clip_timing: null handle");
     DeviceGuard g(m->device);
-    m->timing = enable != 0;
+    m->timing = enable;
     m->ev_n = 0;
     m->gemm_flops = 0;
     if (m->timing && m->ev.empty()) {
-        m->ev.resize(4096);
+        m->ev.resize(8192);
+        m->ev_cat.assign(4096, 0);
         for (auto &e : m->ev) CB_CUDA(cudaEventCreate(&e));
+    }
+    return CB_OK;
+}
+
+int cb_clip_timing_breakdown(cb_clip *m, double *ms_by_class4) {
+    CB_REQUIRE(m && ms_by_class4, "cb_clip_timing_breakdown: null argument");
+    DeviceGuard g(m->device);
+    for (int i = 0; i < 4; i++) ms_by_class4[i] = 0;
+    for (int i = 0; i + 1 < m->ev_n; i += 2) {
+        CB_CUDA(cudaEventSynchronize(m->ev[i + 1]));
+        float ms = 0;
+        CB_CUDA(cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]));
+        ms_by_class4[m->ev_cat[i / 2] & 3] += ms;
     }
     return CB_OK;
 }
@@ -478,15 +586,18 @@ int cb_clip_timing_read(cb_clip *m, double *gemm_ms_total, double *gemm_flops, i
     CB_REQUIRE(m && gemm_ms_total && gemm_flops && n_gemms, "cb_clip_timing_read: null argument");
     DeviceGuard g(m->device);
     double tot = 0;
+    int ng = 0;
     for (int i = 0; i + 1 < m->ev_n; i += 2) {
+        if (m->ev_cat[i / 2] != 0) continue;
         CB_CUDA(cudaEventSynchronize(m->ev[i + 1]));
         float ms = 0;
         CB_CUDA(cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]));
         tot += ms;
+        ng++;
     }
     *gemm_ms_total = tot;
     *gemm_flops = m->gemm_flops;
-    *n_gemms = m->ev_n / 2;
+    *n_gemms = ng;
     m->ev_n = 0;
     m->gemm_flops = 0;
     return CB_OK;

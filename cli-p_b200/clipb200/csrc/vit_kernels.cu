@@ -83,18 +83,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
 
-    // per-lane slice of gamma / beta stays in registers across rows
-    float g[NV * 8], bt[NV * 8];
-#pragma unroll
-    for (int c = 0; c < NV; c++) {
-        const int col = (lane + 32 * c) * 8;
-        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + col) + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + col)), b1 = __ldg(reinterpret_cast<const float4 *>(beta + col) + 1);
-        g[c * 8 + 0] = g0.x; g[c * 8 + 1] = g0.y; g[c * 8 + 2] = g0.z; g[c * 8 + 3] = g0.w;
-        g[c * 8 + 4] = g1.x; g[c * 8 + 5] = g1.y; g[c * 8 + 6] = g1.z; g[c * 8 + 7] = g1.w;
-        bt[c * 8 + 0] = b0.x; bt[c * 8 + 1] = b0.y; bt[c * 8 + 2] = b0.z; bt[c * 8 + 3] = b0.w;
-        bt[c * 8 + 4] = b1.x; bt[c * 8 + 5] = b1.y; bt[c * 8 + 6] = b1.z; bt[c * 8 + 7] = b1.w;
-    }
     auto src_row = [&](int r) -> int64_t { return gather ? (int64_t)gather[r] : (int64_t)r * in_row_stride; };
     auto load = [&](uint4 (&u)[NV], int64_t in_row) {
         const uint4 *p = reinterpret_cast<const uint4 *>(in + in_row * W);
@@ -140,9 +128,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict
         uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)row * W);
 #pragma unroll
         for (int c = 0; c < NV; c++) {
+            const int col = (lane + 32 * c) * 8;     // gamma/beta: 6 KB, L1-resident after the first row
+            const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + col) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + col)), b1 = __ldg(reinterpret_cast<const float4 *>(beta + col) + 1);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float r[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) r[e] = fmaf((v[c * 8 + e] - mean) * rstd, g[c * 8 + e], bt[c * 8 + e]);
+            for (int e = 0; e < 8; e++) r[e] = fmaf((v[c * 8 + e] - mean) * rstd, g[e], bt[e]);
             o[lane + 32 * c] = make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
         }
 #pragma unroll
@@ -225,7 +218,9 @@ int layernorm_f16(const __half *in, __half *out, const float *gamma, const float
                   int in_row_stride, const int *gather, const float *cls_fill, int cls_period, cudaStream_t s) {
     CB_REQUIRE(width == 768 || width == 512, "layernorm_f16: width %d not supported", width);
     if (rows == 0) return CB_OK;
-    const int grid = std::min((rows + 7) / 8, kNumSMs * 4);
+    int per_sm = 6;
+    if (const char *e = getenv("CLIPB200_LN_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));
+    const int grid = std::min((rows + 7) / 8, kNumSMs * per_sm);
     if (cls_period <= 0) cls_period = 1;
     if (width == 768)
         layernorm_kernel<768><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period);

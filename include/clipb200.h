@@ -140,13 +140,20 @@ int cb_clip_encode_image_f32_device(cb_clip *m, int64_t B, const float *nchw_dev
 int cb_clip_encode_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host,
                             int normalize);
 
-/* Pipelined form of cb_clip_encode_image_u8 for the index-time loop
- * (build-index.py:30-58 re-shaped to batches): submit() queues H2D copy + forward
- * + D2H copy and returns; the copy of batch i+1 overlaps the forward pass of
- * batch i (two staging slots).  out_host is valid after cb_clip_sync().  B <=
- * max_image_batch; host buffers should be pinned and must outlive the sync. */
+/* Pipelined forms for the index-time loop (build-index.py:30-58 re-shaped to
+ * batches): submit() queues the work and returns.  Batches alternate between two
+ * lanes (own activation workspace + streams), so the H2D copy of one batch
+ * overlaps the forward pass of the other and the HBM-bound kernels of one pass
+ * (LayerNorm, attention) overlap the tensor-bound GEMMs of the other.  B <=
+ * max_image_batch.  Host variant: out_host is valid after cb_clip_sync(); host
+ * buffers should be pinned and must outlive the sync.  Device variant: work is
+ * ordered after `after_stream`; cb_clip_join(stream) makes `stream` wait for
+ * all submitted work without blocking the host. */
 int cb_clip_submit_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, float *out_host,
                             int normalize);
+int cb_clip_submit_image_u8_device(cb_clip *m, int64_t B, const uint8_t *hwc_dev, float *out_dev,
+                                   int normalize, void *after_stream);
+int cb_clip_join(cb_clip *m, void *stream);
 int cb_clip_sync(cb_clip *m);
 
 /* text_features = model.encode_text(texts)              query-index.py:108
@@ -159,8 +166,11 @@ int cb_clip_encode_text(cb_clip *m, int64_t B, const int32_t *ids_host, float *o
 
 /* live timing of the GEMM launches inside encode_* (bench.py roofline): summed
  * CUDA-event duration, algorithmic FLOPs (2*M*N*K) and count since enable/read */
-int cb_clip_timing(cb_clip *m, int enable);
+int cb_clip_timing(cb_clip *m, int enable);   /* 0 off, 1 GEMM launches, 2 every kernel class */
 int cb_clip_timing_read(cb_clip *m, double *gemm_ms_total, double *gemm_flops, int *n_gemms);
+/* call before cb_clip_timing_read: summed live duration per kernel class since enable,
+ * ms_by_class4 = {gemm, attention, layernorm, other} (level 2 only for the last three) */
+int cb_clip_timing_breakdown(cb_clip *m, double *ms_by_class4);
 
 /* building blocks of the towers, exported for unit tests (device pointers) */
 int cb_layernorm_f16_device(const void *in, void *out, const float *gamma, const float *beta,
