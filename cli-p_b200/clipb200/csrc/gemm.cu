@@ -66,7 +66,7 @@ using namespace tc;
 template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmArgs g, const int m_tiles, const int n_tiles) {
+                    const GemmArgs g, const int m_tiles, const int n_tiles, const int num_stages) {
     // m_tiles counts (128*NCTA)-row tiles; a cluster of NCTA CTAs owns one tile at a time
     using C = Cfg<BN, NCTA>;
     const uint32_t cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
@@ -130,7 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tma_load_2d_2sm(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN + (int)cta_rank * C::B_ROWS,
                                         &full[stage]);
                     }
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -154,7 +154,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         umma_f16<NCTA>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit<NCTA>(&empty[stage]);    // frees the smem slot (in both CTAs) when the MMAs retire
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit<NCTA>(&tfull[as]);           // accumulator complete -> epilogue (both CTAs)
                 as ^= 1;
@@ -376,7 +376,9 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g, m_tiles, n_tiles));
+    int stages = C::STAGES;
+    if (const char *e = getenv("CLIPB200_GEMM_STAGES")) stages = std::max(2, std::min(C::STAGES, atoi(e)));
+    CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g, m_tiles, n_tiles, stages));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
