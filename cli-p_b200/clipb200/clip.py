@@ -180,6 +180,19 @@ def resize_center_crop(image, n_px: int = 224):
     return image.convert("RGB")
 
 
+def resize_center_crop_device(image_u8: torch.Tensor) -> torch.Tensor:
+    """GPU form of resize_center_crop for a uint8 RGB tensor [h, w, 3] on a CUDA device ->
+    [224, 224, 3] uint8, bit-identical to the Pillow path (cb_resize224_u8_device)."""
+    assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.dim() == 3 and image_u8.shape[2] == 3
+    src = image_u8.contiguous()
+    out = torch.empty((224, 224, 3), dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        stream = C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
+        N.check(N.lib().cb_resize224_u8_device(C.c_void_p(src.data_ptr()), src.shape[0], src.shape[1],
+                                               C.c_void_p(out.data_ptr()), stream))
+    return out
+
+
 def image_to_u8(image, n_px: int = 224) -> np.ndarray:
     """PIL image -> uint8 [n_px, n_px, 3] ready for encode_image's uint8 path."""
     return np.array(resize_center_crop(image, n_px), dtype=np.uint8)

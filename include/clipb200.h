@@ -182,6 +182,14 @@ int cb_preprocess_u8_device(const uint8_t *hwc, void *patches_f16, int B, void *
 int cb_preprocess_f32_device(const float *nchw, void *patches_f16, int B, void *stream);
 int cb_l2norm_f32_device(const float *in, float *out, int rows, int width, void *stream);
 
+/* transform(image), first half                           build-index.py:48
+ * clip._transform's Resize(224, BICUBIC) on the shorter side + CenterCrop(224) for
+ * one uint8 RGB image [h][w][3] already on the device -> [224][224][3] uint8.
+ * Bit-identical to Pillow's ImagingResample (22-bit fixed-point weights,
+ * horizontal then vertical pass); feed the result to cb_clip_encode_image_u8*. */
+int cb_resize224_u8_device(const uint8_t *src_hwc, int h, int w, uint8_t *dst_224x224x3,
+                           void *stream);
+
 /* ---- tcgen05 GEMM building block (exported for unit tests and benches) ----
  * C[M,N] = epilogue(A[M,K] fp16 row-major x W[N,K]^T fp16 row-major), fp32
  * accumulation in tensor memory.  Replaces the cuBLAS calls torch dispatches for
