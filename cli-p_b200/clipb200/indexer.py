@@ -33,6 +33,7 @@ def list_images(base_path: str) -> List[str]:
 
 
 def _decode(tfn: str) -> Optional[np.ndarray]:
+    """PIL decode + the reference's Resize/CenterCrop/RGB on the CPU -> uint8 [224,224,3]."""
     from PIL import Image
     from .clip import image_to_u8
     try:
@@ -44,9 +45,41 @@ def _decode(tfn: str) -> Optional[np.ndarray]:
         return None
 
 
+def _decode_full(tfn: str):
+    """PIL decode only.  RGB images come back at full resolution (uint8 [h,w,3]) for the GPU
+    resize; other modes (L, P, RGBA, ...) must be resized in their own mode before the RGB
+    conversion (clip._transform order), so they take the CPU path and come back as [224,224,3]."""
+    from PIL import Image
+    from .clip import image_to_u8
+    try:
+        with Image.open(tfn) as im:
+            if im.mode == "RGB":
+                return np.array(im, dtype=np.uint8)
+            return image_to_u8(im)
+    except KeyboardInterrupt:
+        raise
+    except Exception:
+        return None
+
+
+def _read_bytes(tfn: str):
+    try:
+        with open(tfn, "rb") as fh:
+            return fh.read()
+    except Exception:
+        return None
+
+
 def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers: Optional[int] = None,
-                  out=sys.stdout) -> Tuple[int, int]:
-    """Embed every new image under `folders` into fn_db.  Returns (embedded, failed)."""
+                  out=sys.stdout, resize: str = "cpu", decode: str = "pil") -> Tuple[int, int]:
+    """Embed every new image under `folders` into fn_db.  Returns (embedded, failed).
+
+    resize="cpu": Pillow resizes (exactly the reference's transform); resize="gpu": full-resolution
+    RGB pixels are uploaded and resized by cb_resize224_u8_device (bit-identical to Pillow).
+    decode="nvjpeg" (implies resize="gpu"): JPEG files are decoded on the GPU by nvjpeg through
+    torchvision (library work; pixels may differ from libjpeg-turbo by +-1)."""
+    if decode == "nvjpeg" or resize == "gpu":
+        return _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode)
     fn_db = env.open_db(b"fn_db")
     skip_db = env.open_db(b"skip_db")
     batch = min(batch, model.max_image_batch)
@@ -113,6 +146,110 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
             for s_, nm_, n_ in inflight:
                 commit(nm_, outs[s_][:n_])
             inflight.clear()
+            print(flush=True, file=out)
+    return n_ok, n_bad
+
+
+def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) -> Tuple[int, int]:
+    import ctypes as C
+    from . import _native as N
+    L = N.lib()
+    fn_db = env.open_db(b"fn_db")
+    skip_db = env.open_db(b"skip_db")
+    batch = min(batch, model.max_image_batch)
+    workers = workers or min(32, os.cpu_count() or 4)
+    dev = model.device
+    n_ok = n_bad = 0
+    nbuf = 3
+    dbuf = [torch.empty((batch, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    dout = [torch.empty((batch, 512), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    use_nvjpeg = decode == "nvjpeg"
+    if use_nvjpeg:
+        import torchvision.io as tvio
+
+    def commit(names, vecs):
+        nonlocal n_ok
+        with env.begin(db=fn_db, write=True) as txn:
+            for name, v in zip(names, vecs.numpy()):
+                txn.put(name.encode(), v.astype("<f4", copy=False).tobytes())
+                print(".", end="", flush=True, file=out)
+                n_ok += 1
+
+    def to_device_224(item, tfn, dst):
+        """item: raw file bytes (nvjpeg) or a decoded array.  Writes [224,224,3] into dst."""
+        if use_nvjpeg and isinstance(item, (bytes, bytearray)):
+            low = tfn.lower()
+            if low.endswith((".jpg", ".jpeg")):
+                data = torch.frombuffer(bytearray(item), dtype=torch.uint8)
+                chw = tvio.decode_jpeg(data, device=dev, mode=tvio.ImageReadMode.RGB)
+                src = chw.permute(1, 2, 0).contiguous()
+            else:
+                px = _decode_full(tfn)
+                if px is None:
+                    return False
+                src = torch.from_numpy(px).to(dev, non_blocking=True)
+        else:
+            src = torch.from_numpy(item).to(dev, non_blocking=True)
+        if tuple(src.shape) == (224, 224, 3):
+            dst.copy_(src)
+        else:
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            N.check(L.cb_resize224_u8_device(C.c_void_p(src.data_ptr()), src.shape[0], src.shape[1],
+                                             C.c_void_p(dst.data_ptr()), stream))
+            src.record_stream(torch.cuda.current_stream(dev))
+        return True
+
+    with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=workers) as pool:
+        for base_path in folders:
+            print(f"CLIPing {base_path}...", file=out)
+            todo = []
+            with env.begin(db=skip_db) as st, env.begin(db=fn_db) as ft:
+                for tfn in list_images(base_path):
+                    key = tfn.encode()
+                    if len(key) > 511 or st.get(key) is not None or ft.get(key) is not None:
+                        continue
+                    todo.append(tfn)
+            inflight = []
+            slot, names, fill = 0, [], 0
+
+            def drain():
+                N.check(L.cb_clip_join(model.handle, model._stream()))
+                for s_, nm_, n_ in inflight:
+                    commit(nm_, dout[s_][:n_].cpu())
+                inflight.clear()
+
+            def flush():
+                nonlocal slot, names, fill
+                if fill == 0:
+                    return
+                N.check(L.cb_clip_submit_image_u8_device(model.handle, fill, C.c_void_p(dbuf[slot].data_ptr()),
+                                                         C.c_void_p(dout[slot].data_ptr()), 1, model._stream()))
+                inflight.append((slot, names, fill))
+                if len(inflight) >= nbuf - 1:
+                    drain()
+                slot = (slot + 1) % nbuf
+                names, fill = [], 0
+
+            loader = _read_bytes if use_nvjpeg else _decode_full
+            for tfn, item in zip(todo, pool.map(loader, todo)):
+                ok = False
+                if item is not None:
+                    try:
+                        ok = to_device_224(item, tfn, dbuf[slot][fill])
+                    except KeyboardInterrupt:
+                        raise
+                    except Exception:
+                        ok = False
+                if not ok:
+                    print("#", end="", flush=True, file=out)
+                    n_bad += 1
+                    continue
+                names.append(tfn)
+                fill += 1
+                if fill == batch:
+                    flush()
+            flush()
+            drain()
             print(flush=True, file=out)
     return n_ok, n_bad
 

@@ -98,3 +98,31 @@ def test_build_index_and_query_against_oracle(tmp_path, monkeypatch):
     s2 = indexer.Searcher(env2, index2, model)
     assert s2.results(feats, k=20, offset=0) == rows
     env2.close()
+
+
+def test_gpu_resize_and_nvjpeg_paths(tmp_path, monkeypatch):
+    """resize="gpu" stores bit-identical vectors to the Pillow path (the CUDA resize is
+    pixel-exact); decode="nvjpeg" agrees to cosine >= 0.999 (nvjpeg vs libjpeg-turbo: +-1 LSB)."""
+    import torch
+    from clipb200 import clip, indexer, lmdb, weights
+    folder = str(tmp_path / "photos") + "/"
+    _make_folder(folder, n=40)
+    sd = weights.synthetic_state_dict(0)
+    model = clip.CLIPB200(sd, device=0, max_image_batch=16, max_text_batch=1)
+    stores = {}
+    for mode, kw in (("cpu", {}), ("gpu", {"resize": "gpu"}), ("nvjpeg", {"decode": "nvjpeg"})):
+        env = lmdb.open(str(tmp_path / f"{mode}.lmdb"), map_size=1 << 30, max_dbs=4)
+        try:
+            ok, bad = indexer.embed_folders([folder], env, model, batch=16, out=io.StringIO(), **kw)
+        except (ImportError, RuntimeError) as e:
+            if mode == "nvjpeg":
+                pytest.skip(f"torchvision nvjpeg decode unavailable: {e}")
+            raise
+        assert (ok, bad) == (40, 1), (mode, ok, bad)
+        with env.begin(db=env.open_db(b"fn_db")) as txn:
+            stores[mode] = {k: np.frombuffer(v, dtype=np.float32) for k, v in txn.cursor()}
+        env.close()
+    assert stores["cpu"].keys() == stores["gpu"].keys() == stores["nvjpeg"].keys()
+    for k in stores["cpu"]:
+        assert np.array_equal(stores["cpu"][k], stores["gpu"][k]), k
+        assert float((stores["cpu"][k] * stores["nvjpeg"][k]).sum()) >= 0.999, k
