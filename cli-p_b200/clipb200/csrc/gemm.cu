@@ -45,15 +45,15 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
     static constexpr int BAR_BYTES = 256;
-    // epilogue staging: per epilogue warp 32 rows x BN/2 fp16, rows padded by 16 B so that both
-    // the row-per-thread accesses and the row-contiguous accesses are bank-conflict free,
-    // followed by the warp's BN/2 fp32 bias (or zero) values
+    // epilogue staging: per epilogue warp 32 rows x BN/2 fp16 as dense boxes of 32 rows x 32
+    // columns (64-byte rows, 64B-swizzled: the layout a TMA store expects, and bank-conflict free
+    // for both row-per-thread and row-contiguous accesses), followed by the warp's BN/2 fp32 bias
     static constexpr int EPI_COLS = BN / 2;
-    static constexpr int EPI_ROW_BYTES = EPI_COLS * 2 + 16;
-    static constexpr int EPI_BIAS_OFF = 32 * EPI_ROW_BYTES;
+    static constexpr int EPI_BOX_BYTES = 32 * 64;
+    static constexpr int EPI_BIAS_OFF = (EPI_COLS / 32) * EPI_BOX_BYTES;
     static constexpr int EPI_WARP_BYTES = EPI_BIAS_OFF + EPI_COLS * 4;
     static constexpr int kMaxSmem = 232448;                   // 227 KB opt-in limit
-    static constexpr int FIXED = BAR_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024;   // + alignment slack
+    static constexpr int FIXED = BAR_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024 + 1024;   // + alignment slack
     static constexpr int STAGES_FIT = (kMaxSmem - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
@@ -66,7 +66,8 @@ using namespace tc;
 template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmArgs g, const int m_tiles, const int n_tiles, const int num_stages) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs g, const int m_tiles, const int n_tiles, const int stages_and_dbg) {
+    const int num_stages = stages_and_dbg & 0xff, dbg_mode = stages_and_dbg >> 8;
     // m_tiles counts (128*NCTA)-row tiles; a cluster of NCTA CTAs owns one tile at a time
     using C = Cfg<BN, NCTA>;
     const uint32_t cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
@@ -167,17 +168,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t as = 0, aphase = 0;
         constexpr int EC = C::EPI_COLS;                  // columns per epilogue warp
         constexpr int CPR = EC / 8;                      // 16-byte chunks per staged row
-        const uint32_t stage_base = smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) +
-                                    (uint32_t)(warp - 2) * C::EPI_WARP_BYTES;
-        const uint32_t bias_smem = stage_base + C::EPI_BIAS_OFF;
-        const uint32_t my_row_smem = stage_base + lane * C::EPI_ROW_BYTES;
+        constexpr bool kTmaStore = EPI != EPI_F32 && EPI != EPI_PATCH;
+        // staging area starts 1024-byte aligned (TMA + swizzle pattern alignment)
+        const uint32_t stage_area = (smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + 1023u) & ~1023u;
+        const uint32_t stage_base = stage_area + (uint32_t)(warp - 2) * C::EPI_BOX_BYTES * (EC / 32);
+        const uint32_t bias_smem = stage_area + kEpiWarps * C::EPI_BOX_BYTES * (EC / 32) + (uint32_t)(warp - 2) * EC * 4;
+        // 16-byte chunk j (of this warp's EC columns) of row r: box j/4, 64-byte rows, 64B swizzle
+        auto stg = [&](int r, int j) -> uint32_t {
+            return stage_base + (uint32_t)(j >> 2) * C::EPI_BOX_BYTES + (uint32_t)r * 64u +
+                   (uint32_t)((((j & 3) ^ ((r >> 1) & 3))) << 4);
+        };
         constexpr bool kHasBias = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID;
+        if (kTmaStore && lane == 0) tma_prefetch_desc(&tmC);
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
             const int row0 = m_blk * BM + q * 32;        // first row of this warp's slice
             const int row = row0 + lane;
             const bool row_ok = row < g.M;
             const int n_base = n_blk * BN + half * EC;   // first column of this warp's slice
+            if (kTmaStore) {
+                // the previous tile's bulk stores must have finished reading the staging boxes
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
             // -- before the accumulator is ready: stage bias and (coalesced, async) the residual
             if (kHasBias) {
                 for (int j = lane; j < EC / 4; j += 32) {
@@ -190,14 +203,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int c = lane; c < 32 * CPR; c += 32) {
                     const int r = c / CPR, j = c - r * CPR;
                     if (row0 + r < g.M)
-                        cp_async16(stage_base + r * C::EPI_ROW_BYTES + j * 16,
-                                   g.resid + (size_t)(row0 + r) * g.N + n_base + j * 8);
+                        cp_async16(stg(r, j), g.resid + (size_t)(row0 + r) * g.N + n_base + j * 8);
                 }
             }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             if (EPI == EPI_BIAS_RESID) cp_async_wait_all();
             __syncwarp();
+            if (dbg_mode == 1) {      // experiment: MMA-only throughput (results are not written)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (NCTA == 1) mbar_arrive_relaxed(&tempty[as]);
+                    else mbar_arrive_cluster(&tempty[as], 0);
+                }
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+                continue;
+            }
             const float *pos_row = nullptr;
             if (EPI == EPI_PATCH) {
                 const int img = row / 49, p = row - img * 49;
@@ -230,15 +253,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint4 rz[4];
                 if (EPI == EPI_BIAS_RESID) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) rz[j] = lds128(my_row_smem + c * 64 + j * 16);
+                    for (int j = 0; j < 4; j++) rz[j] = lds128(stg(lane, c * 4 + j));
                 }
                 tmem_ld_wait();
                 float o[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) o[j] = __uint_as_float(v[j]) + add[j];
                 if (EPI == EPI_BIAS_GELU) {
+                    // QuickGELU x*sigmoid(1.702x) = 0.5x + 0.5x*tanh(0.851x): one SFU op per element
 #pragma unroll
-                    for (int j = 0; j < 32; j++) o[j] = __fdividef(o[j], 1.0f + __expf(-1.702f * o[j]));
+                    for (int j = 0; j < 32; j++) {
+                        float t;
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * o[j]));
+                        const float hx = 0.5f * o[j];
+                        o[j] = fmaf(hx, t, hx);
+                    }
                 }
                 if (EPI == EPI_BIAS_RESID) {
 #pragma unroll
@@ -259,10 +288,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < 8; j++) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     }
                 } else {
-                    // stage the fp16 row slice; the coalesced copy-out happens after the loop
+                    // stage the fp16 row slice in the swizzled box of this 32-column chunk
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        sts128(my_row_smem + c * 64 + j * 16,
+                        sts128(stg(lane, c * 4 + j),
                                make_uint4(pack_h2(o[8 * j], o[8 * j + 1]), pack_h2(o[8 * j + 2], o[8 * j + 3]),
                                           pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7])));
                 }
@@ -276,30 +305,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             as ^= 1;
             if (as == 0) aphase ^= 1;
-            if (EPI != EPI_F32) {
-                // coalesced copy-out: consecutive lanes write consecutive 16-byte chunks of a row
-                __half *Cb = reinterpret_cast<__half *>(g.C);
-                constexpr int ITERS = CPR;               // 32*CPR chunks / 32 lanes
+            if (kTmaStore && dbg_mode != 2) {
+                // bulk-store the staged boxes: the TMA engine writes full rows (rows >= M are clipped),
+                // the warp moves on to the next tile at once
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
 #pragma unroll
-                for (int i0 = 0; i0 < ITERS; i0 += 4) {
-                    uint4 val[4];
-                    int orow[4], jj[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int c = (i0 + u) * 32 + lane;
-                        const int r = c / CPR, j = c - r * CPR;
-                        const int grow = row0 + r;
-                        jj[u] = j;
-                        orow[u] = grow < g.M ? (EPI == EPI_PATCH ? grow + grow / 49 + 1 : grow) : -1;
-                        val[u] = lds128(stage_base + r * C::EPI_ROW_BYTES + j * 16);
+                    for (int bx = 0; bx < EC / 32; bx++) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(stage_base + bx * C::EPI_BOX_BYTES),
+                                       "r"(n_base + bx * 32), "r"(row0)
+                                     : "memory");
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (orow[u] >= 0)
-                            *reinterpret_cast<uint4 *>(Cb + (size_t)orow[u] * g.ldc + n_base + jj[u] * 8) = val[u];
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                __syncwarp();                            // staging buffer is reused by the next tile
+            } else if (EPI == EPI_PATCH) {
+                // scattered rows (class-token gaps): coalesced manual copy-out from the staged boxes
+                __half *Cb = reinterpret_cast<__half *>(g.C);
+                for (int c = lane; c < 32 * CPR; c += 32) {
+                    const int r = c / CPR, j = c - r * CPR;
+                    const int grow = row0 + r;
+                    if (grow < g.M) {
+                        const uint4 val = lds128(stg(r, j));
+                        *reinterpret_cast<uint4 *>(Cb + (size_t)(grow + grow / 49 + 1) * g.ldc + n_base + j * 8) = val;
+                    }
+                }
+                __syncwarp();                            // staging boxes are reused by the next tile
             }
+        }
+        if (kTmaStore) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
         }
     }
 
@@ -345,6 +382,22 @@ int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uin
     return CB_OK;
 }
 
+// output map for the epilogue's bulk stores: fp16 [rows, cols], box = 32 rows x 32 columns
+// (64-byte rows), 64B swizzle
+int make_out_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CB_ERR_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)r); return CB_ERR_CUDA; }
+    return CB_OK;
+}
+
 template <int BN, int EPI, int NCTA>
 int launch(const GemmArgs &g, cudaStream_t s) {
     using C = Cfg<BN, NCTA>;
@@ -359,6 +412,11 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     if (rc) return rc;
     rc = make_map(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, C::B_ROWS);
     if (rc) return rc;
+    CUtensorMap tmC = tmA;                     // placeholder when the epilogue does not bulk-store
+    if (EPI != EPI_F32 && EPI != EPI_PATCH) {
+        rc = make_out_map(&tmC, g.C, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldc);
+        if (rc) return rc;
+    }
     const int m_tiles = (g.M + BM * NCTA - 1) / (BM * NCTA), n_tiles = g.N / BN;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
@@ -378,7 +436,8 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     cfg.numAttrs = 1;
     int stages = C::STAGES;
     if (const char *e = getenv("CLIPB200_GEMM_STAGES")) stages = std::max(2, std::min(C::STAGES, atoi(e)));
-    CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g, m_tiles, n_tiles, stages));
+    if (const char *e = getenv("CLIPB200_GEMM_DEBUG")) stages |= atoi(e) << 8;   // perf experiments only
+    CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, m_tiles, n_tiles, stages));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
