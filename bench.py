@@ -198,7 +198,7 @@ def cpu_search_baseline(seconds_budget: float = 12.0):
     def one():
         rc = lib.oracle_flatip_search(C.c_void_p(xb.ctypes.data), 1, C.c_int64(n), DIM, C.c_void_p(xq.ctypes.data),
                                       C.c_int64(1), C.c_int64(TOPK), C.c_void_p(D.ctypes.data),
-                                      C.c_void_p(I.ctypes.data), 0)
+                                      C.c_void_p(I.ctypes.data), os.cpu_count() or 1)   # all host threads
         assert rc == 0
     one()
     reps, t0 = 0, time.perf_counter()
@@ -328,6 +328,7 @@ def cpu_embed_baseline(seconds_budget: float = 20.0):
     import torch
     from oracle import clip_ref
     from clipb200 import weights
+    torch.set_num_threads(os.cpu_count() or 1)        # torchrun pins OMP_NUM_THREADS=1: use every host core
     sd = weights.synthetic_state_dict(0)
     g = torch.Generator().manual_seed(0)
     x32 = clip_ref.preprocess_u8(torch.randint(0, 256, (32, 224, 224, 3), generator=g, dtype=torch.uint8))

@@ -53,9 +53,11 @@ struct Ws {
 struct Lane {
     Ws ws;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    uint8_t *img = nullptr;
-    float *out = nullptr;
-    cudaEvent_t copied = nullptr, done = nullptr;
+    uint8_t *img[2] = {nullptr, nullptr};   // two input slots: the copy of this lane's next batch does
+    float *out = nullptr;                   // not have to wait for its current forward pass
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, done = nullptr;
+    bool slot_used[2] = {false, false};
+    int n_host = 0;
     bool used = false;
 };
 
@@ -306,8 +308,12 @@ void cb_clip_free(cb_clip *m) {
     for (Lane &l : m->lanes) {
         if (l.stream) cudaStreamSynchronize(l.stream);
         free_ws(l.ws);
-        cudaFree(l.img); cudaFree(l.out);
-        if (l.copied) cudaEventDestroy(l.copied);
+        cudaFree(l.out);
+        for (int i = 0; i < 2; i++) {
+            cudaFree(l.img[i]);
+            if (l.copied[i]) cudaEventDestroy(l.copied[i]);
+            if (l.consumed[i]) cudaEventDestroy(l.consumed[i]);
+        }
         if (l.done) cudaEventDestroy(l.done);
         if (l.copy_stream) cudaStreamDestroy(l.copy_stream);
         if (l.stream) cudaStreamDestroy(l.stream);
@@ -467,9 +473,12 @@ static int lanes_init(cb_clip *m) {
         if (e != cudaSuccess) { set_error("lane workspace: %s", cudaGetErrorString(e)); return CB_ERR_OOM; }
         CB_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         CB_CUDA(cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking));
-        CB_CUDA(cudaMalloc(&l.img, (size_t)std::max(m->max_img, 1) * img_bytes));
+        for (int i = 0; i < 2; i++) {
+            CB_CUDA(cudaMalloc(&l.img[i], (size_t)std::max(m->max_img, 1) * img_bytes));
+            CB_CUDA(cudaEventCreateWithFlags(&l.copied[i], cudaEventDisableTiming));
+            CB_CUDA(cudaEventCreateWithFlags(&l.consumed[i], cudaEventDisableTiming));
+        }
         CB_CUDA(cudaMalloc(&l.out, (size_t)std::max(m->max_img, 1) * ED * 4));
-        CB_CUDA(cudaEventCreateWithFlags(&l.copied, cudaEventDisableTiming));
         CB_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
     }
     CB_CUDA(cudaEventCreateWithFlags(&m->fence_ev, cudaEventDisableTiming));
@@ -486,14 +495,20 @@ int cb_clip_submit_image_u8(cb_clip *m, int64_t B, const uint8_t *hwc_host, floa
     if (rc) return rc;
     Lane &l = m->lanes[m->next_lane];
     m->next_lane ^= 1;
-    // this lane's previous forward pass must have consumed its input before we overwrite it
-    if (l.used) CB_CUDA(cudaStreamWaitEvent(l.copy_stream, l.done, 0));
-    CB_CUDA(cudaMemcpyAsync(l.img, hwc_host, (size_t)B * 224 * 224 * 3, cudaMemcpyHostToDevice, l.copy_stream));
-    CB_CUDA(cudaEventRecord(l.copied, l.copy_stream));
-    CB_CUDA(cudaStreamWaitEvent(l.stream, l.copied, 0));
-    if ((rc = encode_u8_chunk(m, l.ws, (int)B, l.img, l.out, normalize, l.stream))) return rc;
+    const int sl = l.n_host & 1;
+    l.n_host++;
+    // the forward pass that last read this input slot (two submissions ago on this lane) must be
+    // past its preprocess kernel before the slot is overwritten
+    if (l.slot_used[sl]) CB_CUDA(cudaStreamWaitEvent(l.copy_stream, l.consumed[sl], 0));
+    CB_CUDA(cudaMemcpyAsync(l.img[sl], hwc_host, (size_t)B * 224 * 224 * 3, cudaMemcpyHostToDevice, l.copy_stream));
+    CB_CUDA(cudaEventRecord(l.copied[sl], l.copy_stream));
+    CB_CUDA(cudaStreamWaitEvent(l.stream, l.copied[sl], 0));
+    if ((rc = timed_other(m, 3, l.stream, [&] { return preprocess_u8(l.img[sl], l.ws.patches, (int)B, l.stream); }))) return rc;
+    CB_CUDA(cudaEventRecord(l.consumed[sl], l.stream));      // pixels are in the im2col buffer now
+    if ((rc = vision_from_patches(m, l.ws, (int)B, l.out, normalize, l.stream))) return rc;
     CB_CUDA(cudaMemcpyAsync(out_host, l.out, (size_t)B * ED * 4, cudaMemcpyDeviceToHost, l.stream));
     CB_CUDA(cudaEventRecord(l.done, l.stream));
+    l.slot_used[sl] = true;
     l.used = true;
     return CB_OK;
 }
