@@ -70,6 +70,8 @@ SIGNATURES = {
     "cb_preprocess_f32_device": (_int, [_p, _p, _int, _p]),
     "cb_l2norm_f32_device": (_int, [_p, _p, _int, _int, _p]),
     "cb_resize224_u8_device": (_int, [_p, _int, _int, _p, _p]),
+    "cb_gemm_f16_ex_device": (_int, [_int, _int, _int, _p, _p, _p, _p, _p, _int, _p, _int, _p, _p, _p]),
+    "cb_gemm_out_slices": (_int, [_int, _int]),
     "cb_gemm_f16_device": (_int, [_int, _int, _int, _p, _p, _p, _p, _p, _p, _int, _int, _p]),
     "cb_flatip_batch_stats": (_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "cb_flatip_timing": (_int, [_p, _int]),

@@ -37,6 +37,9 @@ struct Param {
 struct LayerW {
     const __half *w_qkv, *w_o, *w_fc, *w_proj;
     const float *b_qkv, *b_o, *b_fc, *b_proj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    // LayerNorm-folded form (gemm.cuh): w_qkv / w_fc hold gamma-scaled weights, b_qkv / b_fc the
+    // beta-corrected biases, cs_* the per-output-column sums of the scaled weights
+    const float *cs_qkv = nullptr, *cs_fc = nullptr;
 };
 
 constexpr int VW = 768, VL = 50, VH = 12, TW = 512, TL = 77, TH = 8, LAYERS = 12, ED = 512, VOCAB = 49408;
@@ -46,7 +49,10 @@ struct Ws {
     __half *patches = nullptr, *x = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *cls = nullptr;
     float *emb = nullptr;
     int *eot = nullptr;
+    float *st1 = nullptr, *st2 = nullptr;   // per-row (sum, sum^2) slices for the folded ln_1 / ln_2
 };
+
+constexpr int kMaxStatSlices = 16;
 
 // a lane = workspace + streams + staging for the pipelined submit API; two lanes run
 // concurrently so the memory-bound kernels of one batch overlap the GEMMs of the other
@@ -67,6 +73,8 @@ struct cb_clip {
     int device = 0;
     int max_img = 0, max_txt = 0;
     std::map<std::string, Param> params;
+    std::map<std::string, std::vector<float>> host;   // fp32 copies needed to fold LayerNorm at finalize
+    bool ln_fold = true;          // CLIPB200_NO_LN_FOLD=1 keeps separate LayerNorm launches
     bool finalized = false;
     LayerW vis[LAYERS], txt[LAYERS];
     const __half *conv1_w = nullptr, *vproj_w = nullptr, *tproj_w = nullptr;
@@ -129,6 +137,53 @@ int need(cb_clip *m, const std::string &name, int64_t numel, bool half, const T 
     return CB_OK;
 }
 
+// W'[n][k] = gamma[k] W[n][k] (rounded to fp16), colsum[n] = sum_k W'[n][k] (of the rounded values),
+// b'[n] = b[n] + sum_k beta[k] W[n][k]; replaces the raw weight / bias on the device
+int fold_one(cb_clip *m, const std::string &wname, const std::string &bname, const std::string &gname,
+             const std::string &btname, const std::string &csname, int N, int K) {
+    auto need_host = [&](const std::string &n, size_t cnt) -> const std::vector<float> * {
+        auto it = m->host.find(n);
+        if (it == m->host.end() || it->second.size() != cnt) return nullptr;
+        return &it->second;
+    };
+    const std::vector<float> *Wv = need_host(wname, (size_t)N * K), *bv = need_host(bname, N);
+    const std::vector<float> *gv = need_host(gname, K), *btv = need_host(btname, K);
+    if (!Wv || !bv || !gv || !btv) {
+        set_error("cb_clip_finalize: %s / %s / %s / %s missing or mis-sized", wname.c_str(), bname.c_str(),
+                  gname.c_str(), btname.c_str());
+        return CB_ERR_INVALID;
+    }
+    std::vector<float> Wf((size_t)N * K), cs(N), bf(N);
+    for (int n = 0; n < N; n++) {
+        double s_cs = 0.0, s_b = 0.0;
+        const float *wr = Wv->data() + (size_t)n * K;
+        for (int k = 0; k < K; k++) {
+            const float wp = __half2float(__float2half_rn((*gv)[k] * wr[k]));
+            Wf[(size_t)n * K + k] = wp;
+            s_cs += wp;
+            s_b += (double)(*btv)[k] * wr[k];
+        }
+        cs[n] = (float)s_cs;
+        bf[n] = (*bv)[n] + (float)s_b;
+    }
+    int rc;
+    if ((rc = upload(m, wname, Wf.data(), (int64_t)N * K, true))) return rc;
+    if ((rc = upload(m, bname, bf.data(), N, false))) return rc;
+    return upload(m, csname, cs.data(), N, false);
+}
+
+int fold_layernorm(cb_clip *m, const char *prefix, int W) {
+    for (int i = 0; i < LAYERS; i++) {
+        const std::string b = std::string(prefix) + ".resblocks." + std::to_string(i) + ".";
+        int rc;
+        if ((rc = fold_one(m, b + "attn.in_proj_weight", b + "attn.in_proj_bias", b + "ln_1.weight", b + "ln_1.bias",
+                           b + "attn.in_proj_colsum", 3 * W, W))) return rc;
+        if ((rc = fold_one(m, b + "mlp.c_fc.weight", b + "mlp.c_fc.bias", b + "ln_2.weight", b + "ln_2.bias",
+                           b + "mlp.c_fc_colsum", 4 * W, W))) return rc;
+    }
+    return CB_OK;
+}
+
 int bind_blocks(cb_clip *m, const char *prefix, int W, LayerW *lw) {
     for (int i = 0; i < LAYERS; i++) {
         const std::string b = std::string(prefix) + ".resblocks." + std::to_string(i) + ".";
@@ -145,6 +200,10 @@ int bind_blocks(cb_clip *m, const char *prefix, int W, LayerW *lw) {
         rc |= need(m, b + "ln_1.bias", W, false, &lw[i].ln1_b);
         rc |= need(m, b + "ln_2.weight", W, false, &lw[i].ln2_g);
         rc |= need(m, b + "ln_2.bias", W, false, &lw[i].ln2_b);
+        if (m->ln_fold) {
+            rc |= need(m, b + "attn.in_proj_colsum", 3ll * W, false, &lw[i].cs_qkv);
+            rc |= need(m, b + "mlp.c_fc_colsum", 4ll * W, false, &lw[i].cs_fc);
+        }
         if (rc) return CB_ERR_INVALID;
     }
     return CB_OK;
@@ -189,12 +248,41 @@ GemmArgs mk(const __half *A, const __half *W, const float *bias, const __half *r
 // 12 residual attention blocks over x [B*L, W] (in place)
 int run_blocks(cb_clip *m, Ws &w, const LayerW *lw, int W, int heads, int B, int L, bool causal, cudaStream_t s) {
     const int rows = B * L;
+    // perf experiments only (results become wrong): CLIPB200_SKIP=1 drops ln_1/ln_2, =2 drops attention
+    static const int skip = getenv("CLIPB200_SKIP") ? atoi(getenv("CLIPB200_SKIP")) : 0;
+    if (m->ln_fold) {
+        // ln_1 / ln_2 live inside the QKV / c_fc GEMMs: A operand = raw residual stream, per-row
+        // statistics come from whoever wrote x last (ln_pre / text_embed for block 0, then the
+        // residual GEMM epilogues), w.st1 feeds ln_1 and w.st2 feeds ln_2
+        const int res_slices = gemm_out_slices(rows, W);
+        for (int i = 0; i < LAYERS; i++) {
+            int rc;
+            GemmArgs g = mk(w.x, lw[i].w_qkv, lw[i].b_qkv, nullptr, w.qkv, rows, 3 * W, W, EPI_BIAS);
+            g.ln_stats = w.st1; g.ln_slices = i == 0 ? 1 : res_slices; g.colsum = lw[i].cs_qkv;
+            if ((rc = timed_gemm(m, g, s))) return rc;
+            if (!(skip & 2))
+            if ((rc = timed_other(m, 1, s, [&] { return attention_f16(w.qkv, w.att, B, L, heads, causal, s); }))) return rc;
+            g = mk(w.att, lw[i].w_o, lw[i].b_o, w.x, w.x, rows, W, W, EPI_BIAS_RESID);
+            g.stats_out = w.st2;
+            if ((rc = timed_gemm(m, g, s))) return rc;
+            g = mk(w.x, lw[i].w_fc, lw[i].b_fc, nullptr, w.mlp, rows, 4 * W, W, EPI_BIAS_GELU);
+            g.ln_stats = w.st2; g.ln_slices = res_slices; g.colsum = lw[i].cs_fc;
+            if ((rc = timed_gemm(m, g, s))) return rc;
+            g = mk(w.mlp, lw[i].w_proj, lw[i].b_proj, w.x, w.x, rows, W, 4 * W, EPI_BIAS_RESID);
+            g.stats_out = w.st1;
+            if ((rc = timed_gemm(m, g, s))) return rc;
+        }
+        return CB_OK;
+    }
     for (int i = 0; i < LAYERS; i++) {
         int rc;
+        if (!(skip & 1))
         if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.h, lw[i].ln1_g, lw[i].ln1_b, rows, W, 1, nullptr, nullptr, 0, s); }))) return rc;
         if ((rc = timed_gemm(m, mk(w.h, lw[i].w_qkv, lw[i].b_qkv, nullptr, w.qkv, rows, 3 * W, W, EPI_BIAS), s))) return rc;
+        if (!(skip & 2))
         if ((rc = timed_other(m, 1, s, [&] { return attention_f16(w.qkv, w.att, B, L, heads, causal, s); }))) return rc;
         if ((rc = timed_gemm(m, mk(w.att, lw[i].w_o, lw[i].b_o, w.x, w.x, rows, W, W, EPI_BIAS_RESID), s))) return rc;
+        if (!(skip & 1))
         if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.h, lw[i].ln2_g, lw[i].ln2_b, rows, W, 1, nullptr, nullptr, 0, s); }))) return rc;
         if ((rc = timed_gemm(m, mk(w.h, lw[i].w_fc, lw[i].b_fc, nullptr, w.mlp, rows, 4 * W, W, EPI_BIAS_GELU), s))) return rc;
         if ((rc = timed_gemm(m, mk(w.mlp, lw[i].w_proj, lw[i].b_proj, w.x, w.x, rows, W, 4 * W, EPI_BIAS_RESID), s))) return rc;
@@ -214,11 +302,13 @@ cudaError_t alloc_ws(const cb_clip *m, Ws &w) {
     A((void **)&w.x, n_x * 2); A((void **)&w.h, n_x * 2); A((void **)&w.att, n_x * 2);
     A((void **)&w.qkv, 3 * n_x * 2); A((void **)&w.mlp, 4 * n_x * 2);
     A((void **)&w.cls, n_cls * 2); A((void **)&w.emb, nb * ED * 4); A((void **)&w.eot, nb * 4);
+    const size_t rows = std::max(rows_v, rows_t);
+    A((void **)&w.st1, rows * kMaxStatSlices * 8); A((void **)&w.st2, rows * kMaxStatSlices * 8);
     return e;
 }
 
 void free_ws(Ws &w) {
-    void *bufs[] = {w.patches, w.x, w.h, w.qkv, w.att, w.mlp, w.cls, w.emb, w.eot};
+    void *bufs[] = {w.patches, w.x, w.h, w.qkv, w.att, w.mlp, w.cls, w.emb, w.eot, w.st1, w.st2};
     for (void *p : bufs) cudaFree(p);
     w = Ws();
 }
@@ -230,7 +320,8 @@ int vision_from_patches(cb_clip *m, Ws &w, int B, float *out_dev, int normalize,
     g.pos = m->vpos;
     if ((rc = timed_gemm(m, g, s))) return rc;
     // ln_pre in place; class-token rows (row % 50 == 0) come from class_embedding + pos[0]
-    if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.x, m->ln_pre_g, m->ln_pre_b, B * VL, VW, 1, nullptr, m->cls_pos, VL, s); }))) return rc;
+    if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.x, m->ln_pre_g, m->ln_pre_b, B * VL, VW, 1, nullptr, m->cls_pos, VL, s,
+                                                                  m->ln_fold ? w.st1 : nullptr); }))) return rc;
     if ((rc = run_blocks(m, w, m->vis, VW, VH, B, VL, false, s))) return rc;
     if ((rc = layernorm_f16(w.x, w.cls, m->ln_post_g, m->ln_post_b, B, VW, VL, nullptr, nullptr, 0, s))) return rc;
     float *emb = normalize ? w.emb : out_dev;
@@ -247,7 +338,7 @@ int encode_u8_chunk(cb_clip *m, Ws &w, int b, const uint8_t *hwc_dev, float *out
 
 int text_forward(cb_clip *m, Ws &w, int B, const int32_t *ids_dev, float *out_dev, int normalize, cudaStream_t s) {
     int rc;
-    if ((rc = text_embed(ids_dev, m->tok_emb, m->tpos, w.x, w.eot, B, TL, TW, VOCAB, s))) return rc;
+    if ((rc = text_embed(ids_dev, m->tok_emb, m->tpos, w.x, w.eot, B, TL, TW, VOCAB, s, m->ln_fold ? w.st1 : nullptr))) return rc;
     if ((rc = run_blocks(m, w, m->txt, TW, TH, B, TL, true, s))) return rc;
     // ln_final only on the EOT rows (LayerNorm is per-row, so gathering first is exact)
     if ((rc = layernorm_f16(w.x, w.cls, m->lnf_g, m->lnf_b, B, TW, 1, w.eot, nullptr, 0, s))) return rc;
@@ -349,6 +440,11 @@ int cb_clip_set_param(cb_clip *m, const char *name_c, const float *host, int64_t
     }
     const bool gemm_w = ends_with(name, "in_proj_weight") || ends_with(name, "out_proj.weight") ||
                         ends_with(name, "c_fc.weight") || ends_with(name, "c_proj.weight");
+    // everything LayerNorm folding needs at finalize: the two consuming weights + biases and ln_1 / ln_2
+    if (name.find(".resblocks.") != std::string::npos &&
+        (ends_with(name, "in_proj_weight") || ends_with(name, "in_proj_bias") || ends_with(name, "c_fc.weight") ||
+         ends_with(name, "c_fc.bias") || name.find(".ln_1.") != std::string::npos || name.find(".ln_2.") != std::string::npos))
+        m->host[name].assign(host, host + numel);
     return upload(m, name, host, numel, gemm_w);
 }
 
@@ -371,6 +467,12 @@ int cb_clip_finalize(cb_clip *m) {
     rc |= need(m, "ln_final.bias", TW, false, &m->lnf_b);
     rc |= need(m, "text_projection", 1ll * TW * ED, true, &m->tproj_w);
     if (rc) return CB_ERR_INVALID;
+    m->ln_fold = !(getenv("CLIPB200_NO_LN_FOLD") && atoi(getenv("CLIPB200_NO_LN_FOLD")));
+    if (m->ln_fold) {
+        if ((rc = fold_layernorm(m, "visual.transformer", VW))) return rc;
+        if ((rc = fold_layernorm(m, "transformer", TW))) return rc;
+    }
+    m->host.clear();
     if ((rc = bind_blocks(m, "visual.transformer", VW, m->vis))) return rc;
     if ((rc = bind_blocks(m, "transformer", TW, m->txt))) return rc;
     // class token row before ln_pre = class_embedding + positional_embedding[0]

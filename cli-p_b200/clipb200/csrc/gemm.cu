@@ -51,7 +51,7 @@ struct Cfg {
     static constexpr int EPI_COLS = BN / 2;
     static constexpr int EPI_BOX_BYTES = 32 * 64;
     static constexpr int EPI_BIAS_OFF = (EPI_COLS / 32) * EPI_BOX_BYTES;
-    static constexpr int EPI_WARP_BYTES = EPI_BIAS_OFF + EPI_COLS * 4;
+    static constexpr int EPI_WARP_BYTES = EPI_BIAS_OFF + 2 * EPI_COLS * 4;   // + bias and colsum slices
     static constexpr int kMaxSmem = 232448;                   // 227 KB opt-in limit
     static constexpr int FIXED = BAR_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024 + 1024;   // + alignment slack
     static constexpr int STAGES_FIT = (kMaxSmem - FIXED) / STAGE_BYTES;
@@ -61,6 +61,9 @@ struct Cfg {
 };
 
 using namespace tc;
+
+template <int EPI>
+__host__ __device__ constexpr bool kHasBiasT() { return EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID; }
 
 // ---- the kernel -------------------------------------------------------------------------
 template <int BN, int EPI, int NCTA>
@@ -172,7 +175,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // staging area starts 1024-byte aligned (TMA + swizzle pattern alignment)
         const uint32_t stage_area = (smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + 1023u) & ~1023u;
         const uint32_t stage_base = stage_area + (uint32_t)(warp - 2) * C::EPI_BOX_BYTES * (EC / 32);
-        const uint32_t bias_smem = stage_area + kEpiWarps * C::EPI_BOX_BYTES * (EC / 32) + (uint32_t)(warp - 2) * EC * 4;
+        const uint32_t bias_smem = stage_area + kEpiWarps * C::EPI_BOX_BYTES * (EC / 32) + (uint32_t)(warp - 2) * EC * 8;
+        const uint32_t csum_smem = bias_smem + EC * 4;
+        const bool ln_fold = kHasBiasT<EPI>() && g.ln_stats != nullptr;
+        const bool emit_stats = EPI == EPI_BIAS_RESID && g.stats_out != nullptr;
+        const int out_slices = g.N / EC;
         // 16-byte chunk j (of this warp's EC columns) of row r: box j/4, 64-byte rows, 64B swizzle
         auto stg = [&](int r, int j) -> uint32_t {
             return stage_base + (uint32_t)(j >> 2) * C::EPI_BOX_BYTES + (uint32_t)r * 64u +
@@ -198,6 +205,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(bias_smem + j * 16), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
                 }
             }
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (ln_fold) {
+                for (int j = lane; j < EC / 4; j += 32) {
+                    float4 b = __ldg(reinterpret_cast<const float4 *>(g.colsum + n_base) + j);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(csum_smem + j * 16), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+                }
+                if (row_ok) {
+                    const float2 *sp = reinterpret_cast<const float2 *>(g.ln_stats) + (size_t)row * g.ln_slices;
+                    float sx = 0.f, sxx = 0.f;
+                    for (int t = 0; t < g.ln_slices; t++) { float2 p = __ldcg(sp + t); sx += p.x; sxx += p.y; }
+                    const float inv = 1.0f / (float)g.K;
+                    ln_mean = sx * inv;
+                    ln_rstd = rsqrtf(fmaxf(sxx * inv - ln_mean * ln_mean, 0.f) + 1e-5f);
+                }
+            }
+            float st_sum = 0.f, st_sq = 0.f;
             if (EPI == EPI_BIAS_RESID) {
 #pragma unroll 4
                 for (int c = lane; c < 32 * CPR; c += 32) {
@@ -257,8 +280,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 tmem_ld_wait();
                 float o[32];
+                if (ln_fold) {
+                    // y = rstd * (acc - mean * colsum[n]) + b'[n]
+                    const float nrm = -ln_rstd * ln_mean;
 #pragma unroll
-                for (int j = 0; j < 32; j++) o[j] = __uint_as_float(v[j]) + add[j];
+                    for (int j = 0; j < 8; j++) {
+                        float4 cs;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w) : "r"(csum_smem + c * 128 + j * 16));
+                        o[4 * j] = fmaf(ln_rstd, __uint_as_float(v[4 * j]), fmaf(nrm, cs.x, add[4 * j]));
+                        o[4 * j + 1] = fmaf(ln_rstd, __uint_as_float(v[4 * j + 1]), fmaf(nrm, cs.y, add[4 * j + 1]));
+                        o[4 * j + 2] = fmaf(ln_rstd, __uint_as_float(v[4 * j + 2]), fmaf(nrm, cs.z, add[4 * j + 2]));
+                        o[4 * j + 3] = fmaf(ln_rstd, __uint_as_float(v[4 * j + 3]), fmaf(nrm, cs.w, add[4 * j + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] = __uint_as_float(v[j]) + add[j];
+                }
                 if (EPI == EPI_BIAS_GELU) {
                     // QuickGELU x*sigmoid(1.702x) = 0.5x + 0.5x*tanh(0.851x): one SFU op per element
 #pragma unroll
@@ -281,6 +318,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                 }
+                if (emit_stats) {
+                    // row statistics for the next (folded) LayerNorm, from the fp32 values about to be
+                    // rounded to fp16 (the rounding noise is zero-mean, 2^-11 relative per element)
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        st_sum += o[j];
+                        st_sq = fmaf(o[j], o[j], st_sq);
+                    }
+                }
                 if (EPI == EPI_F32) {
                     if (row_ok) {
                         float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.C) + (size_t)row * g.ldc + n0);
@@ -296,6 +342,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                           pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7])));
                 }
             }
+            if (emit_stats && row_ok)
+                reinterpret_cast<float2 *>(g.stats_out)[(size_t)row * out_slices + (n_base / EC)] = make_float2(st_sum, st_sq);
             // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -478,6 +526,15 @@ void pick_config(int M, int N, int sms, int *ncta_out, int *bn_out) {
 
 }  // namespace
 
+int gemm_out_slices(int M, int N) {
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ncta = 1, bn = 128;
+    pick_config(M, N, sms, &ncta, &bn);
+    return N / (bn / 2);
+}
+
 int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
     CB_REQUIRE(g.A && g.W && g.C, "gemm_f16: null operand");
     CB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm_f16: empty shape");
@@ -487,18 +544,23 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
                "gemm_f16: operands must be 16-byte aligned");
     CB_REQUIRE(g.epilogue != EPI_BIAS_RESID || g.resid, "gemm_f16: residual epilogue without residual");
     CB_REQUIRE(g.epilogue != EPI_PATCH || g.pos, "gemm_f16: patch epilogue without pos-emb");
+    CB_REQUIRE(!g.ln_stats || (g.colsum && g.ln_slices > 0 && (g.epilogue == EPI_BIAS || g.epilogue == EPI_BIAS_GELU)),
+               "gemm_f16: LayerNorm fold needs colsum, ln_slices and a bias / bias+GELU epilogue");
+    CB_REQUIRE(!g.stats_out || g.epilogue == EPI_BIAS_RESID, "gemm_f16: stats_out needs the residual epilogue");
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ncta = 1, bn = 128;
     pick_config(g.M, g.N, sms, &ncta, &bn);
-    if (const char *e = getenv("CLIPB200_GEMM_BN")) {
-        int v = atoi(e);
-        if ((v == 128 || v == 192 || v == 256) && g.N % v == 0) bn = v;
-    }
-    if (const char *e = getenv("CLIPB200_GEMM_NCTA")) {
-        int v = atoi(e);
-        if (v == 1 || (v == 2 && g.M > BM)) ncta = v;
+    if (!g.stats_out) {      // test/experiment overrides (the stats layout depends on the default choice)
+        if (const char *e = getenv("CLIPB200_GEMM_BN")) {
+            int v = atoi(e);
+            if ((v == 128 || v == 192 || v == 256) && g.N % v == 0) bn = v;
+        }
+        if (const char *e = getenv("CLIPB200_GEMM_NCTA")) {
+            int v = atoi(e);
+            if (v == 1 || (v == 2 && g.M > BM)) ncta = v;
+        }
     }
     if (ncta == 2) {
         switch (bn) {
@@ -518,6 +580,18 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
 }
 
 }  // namespace cb
+
+extern "C" int cb_gemm_f16_ex_device(int M, int N, int K, const void *A, const void *W, const float *bias,
+                                     const void *resid, void *C, int epilogue, const float *ln_stats, int ln_slices,
+                                     const float *colsum, float *stats_out, void *stream) {
+    cb::GemmArgs g;
+    g.A = (const __half *)A; g.W = (const __half *)W; g.bias = bias; g.resid = (const __half *)resid;
+    g.pos = nullptr; g.C = C; g.M = M; g.N = N; g.K = K; g.ldc = N; g.epilogue = epilogue;
+    g.ln_stats = ln_stats; g.ln_slices = ln_slices; g.colsum = colsum; g.stats_out = stats_out;
+    return cb::gemm_f16(g, (cudaStream_t)stream);
+}
+
+extern "C" int cb_gemm_out_slices(int M, int N) { return cb::gemm_out_slices(M, N); }
 
 extern "C" int cb_gemm_f16_device(int M, int N, int K, const void *A, const void *W, const float *bias,
                                   const void *resid, const float *pos, void *C, int ldc, int epilogue,

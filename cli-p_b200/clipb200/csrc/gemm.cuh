@@ -26,9 +26,25 @@ struct GemmArgs {
     int M, N, K;
     int ldc;             // elements
     int epilogue;
+    // LayerNorm folded into this GEMM (EPI_BIAS / EPI_BIAS_GELU): A holds the RAW residual
+    // stream x, W holds gamma-scaled weights W'[n][k] = gamma[k] W[n][k], bias holds
+    // b'[n] = b[n] + sum_k beta[k] W[n][k], and the epilogue computes
+    //     y = rstd_r * (acc - mean_r * colsum[n]) + b'[n],   colsum[n] = sum_k W'[n][k]
+    // from per-row partial sums ln_stats[r][s] = (sum x, sum x^2) over column slice s
+    // (LayerNorm width = K, eps 1e-5).  Null = plain epilogue.
+    const float *ln_stats = nullptr;
+    int ln_slices = 0;
+    const float *colsum = nullptr;
+    // EPI_BIAS_RESID: also emit the per-row partial (sum, sum of squares) of the output (fp32
+    // values before the fp16 store) over each epilogue warp's column slice: stats_out[r][gemm_out_slices(M,N)][2].
+    // One writer per slot: deterministic, nothing to zero.
+    float *stats_out = nullptr;
 };
 
 // returns a CB_* code; launches on `stream`
 int gemm_f16(const GemmArgs &g, cudaStream_t stream);
+
+// number of column slices a GEMM of this shape writes per row into stats_out
+int gemm_out_slices(int M, int N);
 
 }  // namespace cb

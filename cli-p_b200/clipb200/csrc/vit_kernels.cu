@@ -76,7 +76,8 @@ template <int W>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict__ in, __half *__restrict__ out,
                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
                                                        int rows, int in_row_stride, const int *__restrict__ gather,
-                                                       const float *__restrict__ cls_fill, int cls_period) {
+                                                       const float *__restrict__ cls_fill, int cls_period,
+                                                       float *__restrict__ stats_out) {
     constexpr int NV = W / 256;     // uint4 (8 halfs) per lane
     const int lane = threadIdx.x & 31;
     const int stride = gridDim.x * (blockDim.x >> 5);
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict
         for (int i = 0; i < NV * 8; i++) { float d = v[i] - mean; q = fmaf(d, d, q); }
         const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + 1e-5f);
         uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)row * W);
+        float os = 0.f, oq = 0.f;
 #pragma unroll
         for (int c = 0; c < NV; c++) {
             const int col = (lane + 32 * c) * 8;     // gamma/beta: 6 KB, L1-resident after the first row
@@ -137,6 +139,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict
 #pragma unroll
             for (int e = 0; e < 8; e++) r[e] = fmaf((v[c * 8 + e] - mean) * rstd, g[e], bt[e]);
             o[lane + 32 * c] = make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+            if (stats_out) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const float h = __half2float(__float2half_rn(r[e]));
+                    os += h;
+                    oq = fmaf(h, h, oq);
+                }
+            }
+        }
+        if (stats_out) {
+            os = warp_sum(os);
+            oq = warp_sum(oq);
+            if (lane == 0) reinterpret_cast<float2 *>(stats_out)[row] = make_float2(os, oq);
         }
 #pragma unroll
         for (int c = 0; c < NV; c++) cur[c] = nxt[c];
@@ -167,7 +182,8 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float *__restrict__ i
 // one block per text row (77 tokens), one warp per token in turn
 __global__ void __launch_bounds__(256) text_embed_kernel(const int32_t *__restrict__ ids, const float *__restrict__ tok,
                                                         const float *__restrict__ pos, __half *__restrict__ x,
-                                                        int *__restrict__ eot_row, int ctx, int width, int vocab) {
+                                                        int *__restrict__ eot_row, int ctx, int width, int vocab,
+                                                        float *__restrict__ stats_out) {
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int32_t *row = ids + (size_t)b * ctx;
@@ -191,9 +207,24 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const int32_t *__restri
         const float4 *e = reinterpret_cast<const float4 *>(tok + (size_t)id * width);
         const float4 *p = reinterpret_cast<const float4 *>(pos + (size_t)t * width);
         uint2 *o = reinterpret_cast<uint2 *>(x + ((size_t)b * ctx + t) * width);
+        float os = 0.f, oq = 0.f;
         for (int i = lane; i < n4; i += 32) {
             float4 a = __ldg(e + i), c = __ldg(p + i);
-            o[i] = make_uint2(pack2(a.x + c.x, a.y + c.y), pack2(a.z + c.z, a.w + c.w));
+            const float v[4] = {a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w};
+            o[i] = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+            if (stats_out) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float h = __half2float(__float2half_rn(v[k]));
+                    os += h;
+                    oq = fmaf(h, h, oq);
+                }
+            }
+        }
+        if (stats_out) {
+            os = warp_sum(os);
+            oq = warp_sum(oq);
+            if (lane == 0) reinterpret_cast<float2 *>(stats_out)[(size_t)b * ctx + t] = make_float2(os, oq);
         }
     }
 }
@@ -215,7 +246,8 @@ int preprocess_f32(const float *img, __half *patches, int B, cudaStream_t s) {
     return CB_OK;
 }
 int layernorm_f16(const __half *in, __half *out, const float *gamma, const float *beta, int rows, int width,
-                  int in_row_stride, const int *gather, const float *cls_fill, int cls_period, cudaStream_t s) {
+                  int in_row_stride, const int *gather, const float *cls_fill, int cls_period, cudaStream_t s,
+                  float *stats_out) {
     CB_REQUIRE(width == 768 || width == 512, "layernorm_f16: width %d not supported", width);
     if (rows == 0) return CB_OK;
     int per_sm = 6;
@@ -223,9 +255,9 @@ int layernorm_f16(const __half *in, __half *out, const float *gamma, const float
     const int grid = std::min((rows + 7) / 8, kNumSMs * per_sm);
     if (cls_period <= 0) cls_period = 1;
     if (width == 768)
-        layernorm_kernel<768><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period);
+        layernorm_kernel<768><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period, stats_out);
     else
-        layernorm_kernel<512><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period);
+        layernorm_kernel<512><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period, stats_out);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -237,9 +269,9 @@ int l2norm_rows_f32(const float *in, float *out, int rows, int width, cudaStream
     return CB_OK;
 }
 int text_embed(const int32_t *ids, const float *tok_emb, const float *pos_emb, __half *x, int *eot_row, int B,
-               int ctx, int width, int vocab, cudaStream_t s) {
+               int ctx, int width, int vocab, cudaStream_t s, float *stats_out) {
     if (B == 0) return CB_OK;
-    text_embed_kernel<<<B, 256, 0, s>>>(ids, tok_emb, pos_emb, x, eot_row, ctx, width, vocab);
+    text_embed_kernel<<<B, 256, 0, s>>>(ids, tok_emb, pos_emb, x, eot_row, ctx, width, vocab, stats_out);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -202,6 +202,19 @@ int cb_gemm_f16_device(int M, int N, int K, const void *A, const void *W, const 
                        const void *resid, const float *pos, void *C, int ldc, int epilogue,
                        void *stream);
 
+/* Extended form used by the towers: LayerNorm folded into the GEMM and per-row statistics.
+ *  - ln_stats != NULL (epilogue 0 or 1): A is the RAW residual stream x, W holds
+ *    gamma-scaled weights, bias the beta-corrected bias, colsum[n] = sum_k W[n][k]; the
+ *    epilogue computes rstd_r*(acc - mean_r*colsum[n]) + bias[n] from ln_stats[r][s] =
+ *    (sum x, sum x^2) partial sums over ln_slices column slices (LayerNorm width K, eps 1e-5).
+ *    Replaces ln_1 / ln_2 + in_proj / c_fc of openai/CLIP's ResidualAttentionBlock.
+ *  - stats_out != NULL (epilogue 2): also writes the partial (sum, sum^2) of the fp16-rounded
+ *    output per row and column slice, [M][cb_gemm_out_slices(M,N)][2] floats. */
+int cb_gemm_f16_ex_device(int M, int N, int K, const void *A, const void *W, const float *bias,
+                          const void *resid, void *C, int epilogue, const float *ln_stats,
+                          int ln_slices, const float *colsum, float *stats_out, void *stream);
+int cb_gemm_out_slices(int M, int N);
+
 /* kernel launches issued by this library on the calling thread since the last
  * call with reset != 0 (bench.py's gpu_launches) */
 int64_t cb_launch_count(int reset);

@@ -70,3 +70,17 @@ def test_sass_is_sm100(lib):
     from clipb200 import _native
     out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_reference_import_lines_resolve_to_clipb200():
+    """`import lmdb, clip, faiss` (build-index.py:5-8, query-index.py:6-9) with cli-p_b200/ first on
+    PYTHONPATH must bind to this package, in a fresh interpreter, without a GPU."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "cli-p_b200"))
+    code = ("import lmdb, clip, faiss; "
+            "print(lmdb.open.__module__, clip.load.__module__, faiss.IndexFlatIP.__module__, "
+            "faiss.METRIC_INNER_PRODUCT, callable(faiss.read_index), callable(clip.tokenize))")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["clipb200.lmdb", "clipb200.clip", "clipb200.faiss", "0", "True", "True"]

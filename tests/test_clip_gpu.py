@@ -247,3 +247,23 @@ def test_pipelined_submit_equals_blocking_call(model, golden_inputs):
     for b, o in zip(batches, outs):
         ref = model.encode_image_u8_host(b.numpy(), normalize=True)
         assert np.array_equal(o.numpy(), ref)
+
+
+def test_folded_and_unfolded_layernorm_agree(sd, golden_inputs, monkeypatch):
+    """Default: ln_1/ln_2 folded into the QKV / c_fc GEMMs.  CLIPB200_NO_LN_FOLD=1 keeps separate
+    LayerNorm launches; both must agree with each other and with the oracle."""
+    import torch
+    from clipb200 import clip
+    from oracle import clip_ref
+    images, tokens, _ = golden_inputs
+    folded = clip.CLIPB200(sd, device=0, max_image_batch=4, max_text_batch=4)
+    monkeypatch.setenv("CLIPB200_NO_LN_FOLD", "1")
+    plain = clip.CLIPB200(sd, device=0, max_image_batch=4, max_text_batch=4)
+    monkeypatch.delenv("CLIPB200_NO_LN_FOLD")
+    a, b = folded.encode_image(images.cuda()), plain.encode_image(images.cuda())
+    assert _cos(torch, a, b) >= 0.99995
+    ref = clip_ref.encode_image(sd, clip_ref.preprocess_u8(images))
+    assert _cos(torch, a, ref) >= COS_MIN and _cos(torch, b, ref) >= COS_MIN
+    ta, tb = folded.encode_text(tokens.cuda()), plain.encode_text(tokens.cuda())
+    assert _cos(torch, ta, tb) >= 0.99995
+    assert _cos(torch, ta, clip_ref.encode_text(sd, tokens)) >= COS_MIN

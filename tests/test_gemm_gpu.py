@@ -122,3 +122,48 @@ def test_back_to_back_launches_are_deterministic():
     a = _gemm(torch, A, W).clone()
     for _ in range(3):
         assert torch.equal(_gemm(torch, A, W), a)
+
+
+@pytest.mark.parametrize("M,W,epi", [(12800, 768, EPI_BIAS), (1280 + 50, 768, EPI_BIAS_GELU), (77 * 9, 512, EPI_BIAS)])
+def test_layernorm_folded_into_gemm(M, W, epi):
+    """Producer GEMM (residual epilogue) emits per-row statistics of x; consumer GEMM applies
+    LayerNorm in its epilogue from gamma-folded weights.  Reference: LN(x) @ W^T + b in fp32."""
+    import torch
+    from clipb200 import _native as N
+    g = torch.Generator(device="cuda").manual_seed(M + W)
+    L = N.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    # producer: x = x0 + att @ Wo^T + bo, plus statistics
+    att = (torch.randn((M, W), generator=g, device="cuda") * 0.5).half()
+    Wo = (torch.randn((W, W), generator=g, device="cuda") * W ** -0.5).half()
+    bo = torch.randn((W,), generator=g, device="cuda") * 0.1
+    x = (torch.randn((M, W), generator=g, device="cuda") * 2 + 0.7).half()
+    x_ref = (x.float() + att.float() @ Wo.float().T + bo).half()
+    slices = L.cb_gemm_out_slices(M, W)
+    stats = torch.zeros((M, slices, 2), device="cuda")
+    N.check(L.cb_gemm_f16_ex_device(M, W, W, p(att), p(Wo), p(bo), p(x), p(x), EPI_BIAS_RESID, None, 0, None,
+                                    p(stats), st))
+    torch.cuda.synchronize()
+    assert (x.float() - x_ref.float()).abs().max().item() <= 2e-2
+    tot = stats.sum(dim=1)
+    assert torch.allclose(tot[:, 0], x.float().sum(1), atol=2e-2, rtol=1e-4)
+    assert torch.allclose(tot[:, 1], (x.float() ** 2).sum(1), atol=1e-1, rtol=1e-4)
+    # consumer: y = LN(x) @ W1^T + b1 (optionally QuickGELU), LayerNorm folded
+    Nn = 3 * W
+    W1 = torch.randn((Nn, W), generator=g, device="cuda") * W ** -0.5
+    b1 = torch.randn((Nn,), generator=g, device="cuda") * 0.1
+    gamma = 1 + 0.1 * torch.randn((W,), generator=g, device="cuda")
+    beta = 0.1 * torch.randn((W,), generator=g, device="cuda")
+    Wp = (W1 * gamma[None, :]).half()
+    colsum = Wp.float().sum(1).contiguous()
+    bp = (b1 + W1 @ beta).contiguous()
+    y = torch.empty((M, Nn), dtype=torch.float16, device="cuda")
+    N.check(L.cb_gemm_f16_ex_device(M, Nn, W, p(x), p(Wp), p(bp), None, p(y), epi, p(stats), slices, p(colsum),
+                                    None, st))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (W,), gamma, beta, 1e-5) @ W1.T + b1
+    if epi == EPI_BIAS_GELU:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    err = (y.float() - ref).abs()
+    assert err.max().item() <= 3e-2 and err.mean().item() <= 3e-3, (err.max().item(), err.mean().item())
