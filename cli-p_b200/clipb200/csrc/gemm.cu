@@ -70,7 +70,18 @@ template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g, const int m_tiles, const int n_tiles, const int stages_and_dbg) {
-    const int num_stages = stages_and_dbg & 0xff, dbg_mode = stages_and_dbg >> 8;
+    const int num_stages = stages_and_dbg & 0xff, dbg_mode = (stages_and_dbg >> 8) & 0xff, raster = stages_and_dbg >> 16;
+    // tile -> (m tile, n tile).  raster 0: n fastest (concurrent CTAs share an A tile); 1: m fastest (share a
+    // W tile); g >= 2: groups of g m-tiles, m fastest inside a group (share both)
+    auto decode = [&](int tile, int &mt, int &nt) {
+        if (raster == 0) { mt = tile / n_tiles; nt = tile % n_tiles; }
+        else if (raster == 1) { mt = tile % m_tiles; nt = tile / m_tiles; }
+        else {
+            const int per = raster * n_tiles, grp = tile / per, in = tile - grp * per;
+            const int rows = min(raster, m_tiles - grp * raster);
+            mt = grp * raster + in % rows; nt = in / rows;
+        }
+    };
     // m_tiles counts (128*NCTA)-row tiles; a cluster of NCTA CTAs owns one tile at a time
     using C = Cfg<BN, NCTA>;
     const uint32_t cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
@@ -119,7 +130,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
+                int mt_, nt_;
+                decode(tile, mt_, nt_);
+                const int m_blk = mt_ * NCTA + (int)cta_rank, n_blk = nt_;
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *sa = smem + stage * C::STAGE_BYTES;
@@ -188,7 +201,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         constexpr bool kHasBias = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID;
         if (kTmaStore && lane == 0) tma_prefetch_desc(&tmC);
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
+            int mt_, nt_;
+            decode(tile, mt_, nt_);
+            const int m_blk = mt_ * NCTA + (int)cta_rank, n_blk = nt_;
             const int row0 = m_blk * BM + q * 32;        // first row of this warp's slice
             const int row = row0 + lane;
             const bool row_ok = row < g.M;
@@ -485,6 +500,7 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     int stages = C::STAGES;
     if (const char *e = getenv("CLIPB200_GEMM_STAGES")) stages = std::max(2, std::min(C::STAGES, atoi(e)));
     if (const char *e = getenv("CLIPB200_GEMM_DEBUG")) stages |= atoi(e) << 8;   // perf experiments only
+    if (const char *e = getenv("CLIPB200_GEMM_RASTER")) stages |= atoi(e) << 16;
     CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, m_tiles, n_tiles, stages));
     CB_LAUNCH_CHECK();
     return CB_OK;
