@@ -322,11 +322,11 @@ int flatip_search_batch(BatchWs *w, const void *rows_f16, int64_t n, int device,
     const int nq_pad = (int)((nq + 2 * QM - 1) / (2 * QM) * (2 * QM));
     int rc = batch_ws_ensure(w, nq_pad);
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};       // function attributes are per device
+    if (!attr_done[device & 63]) {
         CB_CUDA(cudaFuncSetAttribute(flatip_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CB_CUDA(cudaFuncSetAttribute(batch_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8));
-        attr_done = true;
+        attr_done[device & 63] = true;
     }
     batch_prep_kernel<<<std::min(nq_pad * 2, kNumSMs * 8), 256, 0, s>>>(q_dev, (int)nq, nq_pad, w->qh, w->thr, w->cnt, w->overflow);
     CB_LAUNCH_CHECK();

@@ -465,10 +465,12 @@ template <int BN, int EPI, int NCTA>
 int launch(const GemmArgs &g, cudaStream_t s) {
     using C = Cfg<BN, NCTA>;
     auto kern = gemm_tcgen05_kernel<BN, EPI, NCTA>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    int cur_dev = 0;
+    CB_CUDA(cudaGetDevice(&cur_dev));
+    static bool attr_done[64] = {false};       // function attributes are per device
+    if (!attr_done[cur_dev & 63]) {
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_done = true;
+        attr_done[cur_dev & 63] = true;
     }
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);

@@ -47,6 +47,13 @@ int get_table(int device, int in_size, int out_size, int start, Table *out) {
     auto key = std::make_tuple(device, in_size, out_size, start);
     auto it = g_tables.find(key);
     if (it != g_tables.end()) { *out = it->second; return CB_OK; }
+    if (g_tables.size() >= 2048) {
+        // bound the cache (a photo library has few distinct sizes; a hostile one does not): wait for
+        // kernels that may still read the old tables, then drop them all
+        CB_CUDA(cudaDeviceSynchronize());
+        for (auto &kv : g_tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.kk); }
+        g_tables.clear();
+    }
     const double scale = (double)in_size / out_size;
     double filterscale = scale < 1.0 ? 1.0 : scale;
     const double support = 2.0 * filterscale;

@@ -267,3 +267,18 @@ def test_folded_and_unfolded_layernorm_agree(sd, golden_inputs, monkeypatch):
     ta, tb = folded.encode_text(tokens.cuda()), plain.encode_text(tokens.cuda())
     assert _cos(torch, ta, tb) >= 0.99995
     assert _cos(torch, ta, clip_ref.encode_text(sd, tokens)) >= COS_MIN
+
+
+def test_model_on_a_second_device(sd, golden_inputs):
+    """A model handle on cuda:1 in a process that already ran on cuda:0 (per-device kernel attributes)."""
+    import torch
+    from clipb200 import clip
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    images, tokens, _ = golden_inputs
+    m0 = clip.CLIPB200(sd, device=0, max_image_batch=4, max_text_batch=4)
+    m1 = clip.CLIPB200(sd, device=1, max_image_batch=4, max_text_batch=4)
+    a = m0.encode_image(images.cuda(0), normalize=True).cpu()
+    b = m1.encode_image(images.cuda(1), normalize=True).cpu()
+    assert torch.equal(a, b)
+    assert torch.equal(m0.encode_text(tokens.cuda(0)).cpu(), m1.encode_text(tokens.cuda(1)).cpu())

@@ -109,3 +109,21 @@ def test_batch_over_logical_shards_equals_single(setup):
     D1, I1 = many.search(xq[:48], 100)
     assert (I0 == I1).all()
     assert (D0.view(np.uint32) == D1.view(np.uint32)).all()
+
+
+def test_batch_path_on_a_second_device():
+    """Kernel attributes (opt-in shared memory) are per device: the tensor-core path must also
+    work on cuda:1 in a process that already used cuda:0."""
+    import torch
+    from clipb200 import faiss
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    xb = synth.unit_rows(20_000, seed=41)
+    xq = synth.unit_rows(32, seed=42)
+    a = faiss.IndexFlatIP(512, storage="f16", devices=[0])
+    b = faiss.IndexFlatIP(512, storage="f16", devices=[1])
+    a.add(xb)
+    b.add(xb)
+    D0, I0 = a.search(xq, 50)
+    D1, I1 = b.search(xq, 50)
+    assert (I0 == I1).all() and (D0.view(np.uint32) == D1.view(np.uint32)).all()
