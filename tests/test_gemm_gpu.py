@@ -124,8 +124,9 @@ def test_back_to_back_launches_are_deterministic():
         assert torch.equal(_gemm(torch, A, W), a)
 
 
+@pytest.mark.parametrize("outlier", [0.0, 60.0])
 @pytest.mark.parametrize("M,W,epi", [(12800, 768, EPI_BIAS), (1280 + 50, 768, EPI_BIAS_GELU), (77 * 9, 512, EPI_BIAS)])
-def test_layernorm_folded_into_gemm(M, W, epi):
+def test_layernorm_folded_into_gemm(M, W, epi, outlier):
     """Producer GEMM (residual epilogue) emits per-row statistics of x; consumer GEMM applies
     LayerNorm in its epilogue from gamma-folded weights.  Reference: LN(x) @ W^T + b in fp32."""
     import torch
@@ -138,17 +139,22 @@ def test_layernorm_folded_into_gemm(M, W, epi):
     att = (torch.randn((M, W), generator=g, device="cuda") * 0.5).half()
     Wo = (torch.randn((W, W), generator=g, device="cuda") * W ** -0.5).half()
     bo = torch.randn((W,), generator=g, device="cuda") * 0.1
-    x = (torch.randn((M, W), generator=g, device="cuda") * 2 + 0.7).half()
+    x = (torch.randn((M, W), generator=g, device="cuda") * 2 + 0.7)
+    x[:, 5] += outlier          # real CLIP residual streams carry a few huge-magnitude channels
+    x[:, 301] -= outlier * 0.5
+    x = x.half()
     x_ref = (x.float() + att.float() @ Wo.float().T + bo).half()
     slices = L.cb_gemm_out_slices(M, W)
     stats = torch.zeros((M, slices, 2), device="cuda")
     N.check(L.cb_gemm_f16_ex_device(M, W, W, p(att), p(Wo), p(bo), p(x), p(x), EPI_BIAS_RESID, None, 0, None,
                                     p(stats), st))
     torch.cuda.synchronize()
-    assert (x.float() - x_ref.float()).abs().max().item() <= 2e-2
+    assert ((x.float() - x_ref.float()).abs() <= 2e-2 + 1e-3 * x_ref.float().abs()).all()
     tot = stats.sum(dim=1)
-    assert torch.allclose(tot[:, 0], x.float().sum(1), atol=2e-2, rtol=1e-4)
-    assert torch.allclose(tot[:, 1], (x.float() ** 2).sum(1), atol=1e-1, rtol=1e-4)
+    # statistics are taken from the fp32 values just before the fp16 store: they differ from the
+    # stored row by its rounding noise (<= 2^-10 relative on the sum of squares, worst case)
+    assert torch.allclose(tot[:, 0], x.float().sum(1), atol=1e-1, rtol=2e-4)
+    assert torch.allclose(tot[:, 1], (x.float() ** 2).sum(1), atol=2e-1, rtol=1.5e-3)
     # consumer: y = LN(x) @ W1^T + b1 (optionally QuickGELU), LayerNorm folded
     Nn = 3 * W
     W1 = torch.randn((Nn, W), generator=g, device="cuda") * W ** -0.5
