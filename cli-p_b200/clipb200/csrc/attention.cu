@@ -43,9 +43,12 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
     constexpr int KT = (L + 15) / 16;   // 16-key steps (= 16-row query tiles = warps)
     constexpr int LP = KT * 16;         // padded sequence
     constexpr int NT = 2 * KT;          // 8-key score tiles
-    __shared__ __align__(16) __half sQ[LP * LDS];
-    __shared__ __align__(16) __half sK[LP * LDS];
-    __shared__ __align__(16) __half sV[LP * LDS];
+    // Shared memory is kept small (23.6 KB at L = 50: 9 CTAs per SM).  Q and K hold only the L real rows; the
+    // padded tile rows of Q (>= L) read on into K and those of K read on into V: garbage there only
+    // reaches query rows that are never stored / keys that are masked.  V keeps LP rows, the padded
+    // ones zero, because P (= 0 there) still multiplies them.
+    __shared__ __align__(16) __half sbuf[(2 * L + LP) * LDS];
+    __half *sQ = sbuf, *sK = sbuf + L * LDS, *sV = sbuf + 2 * L * LDS;
 
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int W = heads * HD;
@@ -59,7 +62,7 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
         if (row < L) {
             const __half *src = qkv + ((size_t)(b * L + row) * 3 + mat) * W + h * HD + ch * 8;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-        } else {
+        } else if (mat == 2) {
             *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
         }
     }
