@@ -305,8 +305,12 @@ def run_search(args, torch, dist, rank, world, local):
     if cnt.value:
         scan_s = tot_ms.value / 1e3 / cnt.value
         ach = (hi - lo) * SEARCH_BYTES_PER_ROW / scan_s / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one scan launch over 10M rows, from the ncu
+        # --set full capture committed as profiles/r01_search_scan_ncu_raw.csv (10.240 GB + 8.8 MB)
+        traffic = 10.249e9 if (hi - lo) == DB_ROWS else None
         res["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                           "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                           "algorithmic_bytes": (hi - lo) * SEARCH_BYTES_PER_ROW,
                            "kernel": "flatip_scan_kernel<1,f16>", "kernel_ms": scan_s * 1e3,
                            "peak_source": peaks["source"] + " (copy bandwidth)"}
     return res, clocks

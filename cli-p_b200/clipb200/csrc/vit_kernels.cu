@@ -22,9 +22,20 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // one thread = 8 consecutive bytes of one image row (672 B = 84 chunks); 12 consecutive
-// threads cover one 32-pixel patch row = 96 contiguous output halfs
+// threads cover one 32-pixel patch row = 96 contiguous output halfs.  A pixel byte has only
+// 256 x 3 possible results, so each block first builds the table fp16((v/255 - mean_c)/std_c)
+// with exact IEEE divisions (bit-identical to torch's ToTensor + Normalize) and the streaming
+// loop is pure load / look-up / store.
 __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t *__restrict__ img,
                                                            __half *__restrict__ patches, int B) {
+    __shared__ __half lut[3][256];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        const float mean = c == 0 ? K_MEAN0 : (c == 1 ? K_MEAN1 : K_MEAN2);
+        const float sd = c == 0 ? K_STD0 : (c == 1 ? K_STD1 : K_STD2);
+        lut[c][v] = __float2half_rn(__fdiv_rn(__fdiv_rn((float)v, 255.0f) - mean, sd));
+    }
+    __syncthreads();
     const int64_t total = (int64_t)B * 224 * 84;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -33,18 +44,16 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t *__res
         const int b = (int)(t / (84 * 224));
         const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(img + ((size_t)(b * 224 + y) * 224) * 3) + xb);
         const uint8_t *px = reinterpret_cast<const uint8_t *>(&raw);
-        float f[8];
+        __half h[8];
         int c = (xb * 8) % 3;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const float mean = c == 0 ? K_MEAN0 : (c == 1 ? K_MEAN1 : K_MEAN2);
-            const float sd = c == 0 ? K_STD0 : (c == 1 ? K_STD1 : K_STD2);
-            f[e] = __fdiv_rn(__fdiv_rn((float)px[e], 255.0f) - mean, sd);
+            h[e] = lut[c][px[e]];
             c = c == 2 ? 0 : c + 1;
         }
         const int gy = y >> 5, py = y & 31, gx = xb / 12, j = xb - gx * 12;
         __half *dst = patches + ((size_t)(b * 49 + gy * 7 + gx)) * 3072 + py * 96 + j * 8;
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(h);
     }
 }
 
