@@ -140,6 +140,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                         tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
                         tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN, &full[stage]);
+                    } else if (dbg_mode == 3 && tile != cluster_id) {
+                        // experiment: traffic of a W-stationary schedule (W loaded for the first tile only;
+                        // results are garbage)
+                        if (leader) mbar_expect_tx(&full[stage], NCTA * C::A_BYTES);
+                        tma_load_2d_2sm(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
                     } else {
                         // both CTAs' bytes are credited to the leader's barrier
                         if (leader) mbar_expect_tx(&full[stage], NCTA * C::STAGE_BYTES);
@@ -208,8 +213,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = row0 + lane;
             const bool row_ok = row < g.M;
             const int n_base = n_blk * BN + half * EC;   // first column of this warp's slice
-            if (kTmaStore) {
-                // the previous tile's bulk stores must have finished reading the staging boxes
+            if (kTmaStore && EPI == EPI_BIAS_RESID) {
+                // the residual prefetch below overwrites every staging box: the previous tile's bulk
+                // stores must have finished reading them
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
             }
@@ -266,6 +272,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
 #pragma unroll 1
             for (int c = 0; c < EC / 32; c++) {
+                if (kTmaStore && EPI != EPI_BIAS_RESID) {
+                    // box c is rewritten below: its bulk store of the previous tile (one group per box, so
+                    // NB - 1 younger groups may still be pending) must have finished reading it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(EC / 32 - 1) : "memory");
+                    __syncwarp();
+                }
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * EC + c * 32, v);
                 const int n0 = n_base + c * 32;
@@ -355,6 +367,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         sts128(stg(lane, c * 4 + j),
                                make_uint4(pack_h2(o[8 * j], o[8 * j + 1]), pack_h2(o[8 * j + 2], o[8 * j + 3]),
                                           pack_h2(o[8 * j + 4], o[8 * j + 5]), pack_h2(o[8 * j + 6], o[8 * j + 7])));
+                    if (kTmaStore && dbg_mode != 2) {
+                        // bulk-store this box at once (rows >= M are clipped by the tensor map); one group
+                        // per box so the next tile can reuse box c while later boxes are still in flight
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(stage_base + c * C::EPI_BOX_BYTES),
+                                           "r"(n0), "r"(row0)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
                 }
             }
             if (emit_stats && row_ok)
@@ -368,22 +393,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             as ^= 1;
             if (as == 0) aphase ^= 1;
-            if (kTmaStore && dbg_mode != 2) {
-                // bulk-store the staged boxes: the TMA engine writes full rows (rows >= M are clipped),
-                // the warp moves on to the next tile at once
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int bx = 0; bx < EC / 32; bx++) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(stage_base + bx * C::EPI_BOX_BYTES),
-                                       "r"(n_base + bx * 32), "r"(row0)
-                                     : "memory");
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            } else if (EPI == EPI_PATCH) {
+            if (EPI == EPI_PATCH) {
                 // scattered rows (class-token gaps): coalesced manual copy-out from the staged boxes
                 __half *Cb = reinterpret_cast<__half *>(g.C);
                 for (int c = lane; c < 32 * CPR; c += 32) {
