@@ -21,17 +21,16 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import struct
 from typing import List, Optional, Sequence
 
 import numpy as np
 
 from . import _native as N
+from . import faiss_io as _io
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 
-_MAGIC = b"CB2FLAT1"
 
 
 def _storage_code(storage) -> int:
@@ -313,41 +312,43 @@ def merge_topk_device(Dall, Iall, k: int, shard_stride_D: int = 0, shard_stride_
 
 
 # ---- index file I/O ---------------------------------------------------------------
-# Own container (faiss's IwFl/IxFI interop is a "next" row):
-#   magic "CB2FLAT1" | u32 d | u32 storage | u64 ntotal | u32 kind (0 flat, 1 ivf shim) |
-#   u32 nlist | u32 nprobe | u32 reserved | rows float32 little-endian [ntotal, d]
+# `images.index` is written and read in faiss's own on-disk format (faiss_io.py; SURVEY 8f
+# row 4), so files travel between faiss and clipb200 in both directions:
+#   IndexFlatIP   -> "IxFI"
+#   IndexIVFFlat  -> "IwFl" with nlist = 1: one inverted list holding every row in id order and a
+#                    one-centroid quantizer.  clipb200 serves IVF by an exact scan, so it has no
+#                    k-means partition to record; a one-list IVF searches exactly in faiss as well.
+# read_index flattens any IwFl file (full or sparse list table, any nlist) back into add order.
 
 def write_index(index, path: str) -> None:
-    flat = index._flat if isinstance(index, IndexIVFFlat) else index
-    kind = 1 if isinstance(index, IndexIVFFlat) else 0
-    nlist = getattr(index, "nlist", 0)
-    nprobe = getattr(index, "nprobe", 0)
-    with open(path, "wb") as fh:
-        fh.write(_MAGIC)
-        fh.write(struct.pack("<IIQIIII", flat.d, flat._storage, flat.ntotal, kind, nlist, nprobe, 0))
-        step = 1 << 16
-        for lo in range(0, flat.ntotal, step):
-            rows = flat.reconstruct_n(lo, min(step, flat.ntotal - lo))
-            fh.write(rows.astype("<f4", copy=False).tobytes())
+    """faiss.write_index(index, "images.index")  (build-index.py:109)."""
+    ivf = isinstance(index, IndexIVFFlat)
+    flat = index._flat if ivf else index
+    if not isinstance(flat, IndexFlatIP):
+        raise TypeError(f"write_index: unsupported index type {type(index).__name__}")
+    if ivf:
+        _io.write_ivf_single_list(path, flat.d, flat.ntotal, flat.reconstruct_n, nprobe=getattr(index, "nprobe", 1))
+    else:
+        _io.write_flat(path, flat.d, flat.ntotal, flat.reconstruct_n)
 
 
 def read_index(path: str, storage=None, devices: Optional[Sequence[int]] = None):
-    with open(path, "rb") as fh:
-        magic = fh.read(8)
-        if magic != _MAGIC:
-            raise RuntimeError(f"{path}: not a clipb200 index file (faiss-format interop is not implemented)")
-        d, st, ntotal, kind, nlist, nprobe, _ = struct.unpack("<IIQIIII", fh.read(32))
-        flat = IndexFlatIP(d, storage=st if storage is None else storage, devices=devices)
-        flat.reserve(ntotal)
-        step = 1 << 16
-        for lo in range(0, ntotal, step):
-            m = min(step, ntotal - lo)
-            buf = fh.read(m * d * 4)
-            if len(buf) != m * d * 4:
-                raise RuntimeError(f"{path}: truncated index file")
-            flat.add(np.frombuffer(buf, dtype="<f4").reshape(m, d).astype(np.float32, copy=False))
+    """faiss.read_index("images.index")  (query-index.py:29).  The rows go to the GPU(s) in id
+    order; `storage` / CLIPB200_STORAGE picks fp32 (default) or fp16 rows in HBM."""
+    try:
+        parsed = _io.parse(path)
+    except _io.FaissFormatError as e:
+        raise RuntimeError(str(e)) from None
+    if parsed.metric != METRIC_INNER_PRODUCT:
+        raise RuntimeError(f"{path}: metric type {parsed.metric} is not supported (CLI-P uses inner product, "
+                           f"build-index.py:80-81)")
+    flat = IndexFlatIP(parsed.d, storage=storage, devices=devices)
+    flat.reserve(parsed.ntotal)
+    for rows in parsed.iter_rows():
+        flat.add(rows)
+    kind, nlist, nprobe = (1 if parsed.kind == "ivf" else 0), parsed.nlist, parsed.nprobe
     if kind == 1:
-        ivf = IndexIVFFlat(flat, d, nlist, METRIC_INNER_PRODUCT)
+        ivf = IndexIVFFlat(flat, flat.d, nlist, METRIC_INNER_PRODUCT)
         ivf.is_trained = True
         ivf.nprobe = nprobe
         return ivf

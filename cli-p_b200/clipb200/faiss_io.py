@@ -177,7 +177,8 @@ class ParsedIndex:
     nprobe: int
     _mm: np.ndarray
     _section: object
-    _row_of_id: Optional[np.ndarray] = None      # ivf only: float index (in units of d) of id i's code
+    _list_of_id: Optional[np.ndarray] = None     # ivf only: index into _section.lists holding id i
+    _pos_of_id: Optional[np.ndarray] = None      # ivf only: position of id i inside that list
 
     def rows(self, lo: int, hi: int) -> np.ndarray:
         """float32 (hi-lo, d) rows of ids lo..hi-1 (a copy, C-contiguous)."""
@@ -187,9 +188,12 @@ class ParsedIndex:
             off = self._section.data_offset + lo * d * 4
             return np.frombuffer(self._mm, dtype="<f4", count=(hi - lo) * d, offset=off).reshape(hi - lo, d).astype(np.float32)
         out = np.empty((hi - lo, d), dtype=np.float32)
-        offs = self._row_of_id[lo:hi]
-        for j, o in enumerate(offs):            # codes of consecutive ids are scattered over lists
-            out[j] = np.frombuffer(self._mm, dtype="<f4", count=d, offset=int(o))
+        which, pos = self._list_of_id[lo:hi], self._pos_of_id[lo:hi]
+        for li in np.unique(which):                 # consecutive ids are scattered over the lists
+            sel = which == li
+            _n, sz, c_off, _i = self._section.lists[int(li)]
+            codes = np.frombuffer(self._mm, dtype="<f4", count=sz * d, offset=c_off).reshape(sz, d)
+            out[sel] = codes[pos[sel]]
         return out
 
     def iter_rows(self, step: int = 1 << 15) -> Iterator[np.ndarray]:
@@ -204,16 +208,18 @@ def parse(path: str) -> ParsedIndex:
     if isinstance(sec, FlatSection):
         return ParsedIndex("flat", sec.d, sec.ntotal, sec.metric, 0, 0, mm, sec)
     # flatten the inverted lists back into id (= add) order
-    row_of_id = np.full(sec.ntotal, -1, dtype=np.int64)
-    for (_li, sz, c_off, i_off) in sec.lists:
+    list_of_id = np.full(sec.ntotal, -1, dtype=np.int32)
+    pos_of_id = np.zeros(sec.ntotal, dtype=np.int64)
+    for k, (_li, sz, _c_off, i_off) in enumerate(sec.lists):
         ids = np.frombuffer(mm, dtype="<i8", count=sz, offset=i_off)
         if sz and (ids.min() < 0 or ids.max() >= sec.ntotal):
             raise FaissFormatError(f"{path}: ids outside 0..ntotal-1 (add_with_ids indexes are not supported; "
                                    f"CLI-P uses sequential add, build-index.py:99,107)")
-        row_of_id[ids] = c_off + np.arange(sz, dtype=np.int64) * sec.code_size
-    if sec.ntotal and row_of_id.min() < 0:
+        list_of_id[ids] = k
+        pos_of_id[ids] = np.arange(sz, dtype=np.int64)
+    if sec.ntotal and list_of_id.min() < 0:
         raise FaissFormatError(f"{path}: inverted lists do not cover every id in 0..{sec.ntotal - 1}")
-    return ParsedIndex("ivf", sec.d, sec.ntotal, sec.metric, sec.nlist, sec.nprobe, mm, sec, row_of_id)
+    return ParsedIndex("ivf", sec.d, sec.ntotal, sec.metric, sec.nlist, sec.nprobe, mm, sec, list_of_id, pos_of_id)
 
 
 # ---- writing -----------------------------------------------------------------------
@@ -251,11 +257,12 @@ def write_ivf_single_list(path: str, d: int, ntotal: int, get_rows: Callable[[in
     holding every row with ids 0..ntotal-1, quantizer = one centroid (the mean row).
 
     clipb200 serves IVF by an exact scan (north star), so it has no k-means partition to
-    write; a one-list IVF is the faithful on-disk form of that (faiss clamps nprobe to nlist).
+    write; a one-list IVF is the faithful on-disk form of that.  nprobe is stored as given (the
+    reference sets 32, query-index.py:30; faiss clamps it to nlist when it searches).
     """
     nlist = 1
     with open(path, "wb") as fh:
-        fh.write(b"IwFl" + _header(d, ntotal, metric) + struct.pack("<QQ", nlist, max(1, min(int(nprobe), nlist))))
+        fh.write(b"IwFl" + _header(d, ntotal, metric) + struct.pack("<QQ", nlist, max(1, int(nprobe))))
         quant_at = fh.tell()
         centroid = np.zeros((1, d), dtype="<f4")
         fh.write(_flat_cc(metric) + _header(d, nlist, metric) + struct.pack("<Q", nlist * d) + centroid.tobytes())

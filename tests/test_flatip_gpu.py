@@ -7,6 +7,7 @@ summation order differs from BLAS).  Both arms see the identical fp16-rounded ro
 """
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -142,12 +143,35 @@ def test_incremental_add_reconstruct_and_file_roundtrip(faiss, tmp_path):
     ivf.nprobe = 32
     path = str(tmp_path / "images.index")
     faiss.write_index(ivf, path)
+    assert open(path, "rb").read(4) == b"IwFl"           # faiss's own IndexIVFFlat container
     back = faiss.read_index(path)
     assert isinstance(back, faiss.IndexIVFFlat) and back.nprobe == 32 and back.ntotal == 3000
     xq = synth.unit_rows(2, seed=4)
     D0, I0 = ivf.search(xq, 21)
     D1, I1 = back.search(xq, 21)
     assert (I0 == I1).all() and (D0 == D1).all()
+    # plain flat index -> "IxFI"; fp16 storage on the way back in
+    fpath = str(tmp_path / "flat.index")
+    faiss.write_index(index, fpath)
+    assert open(fpath, "rb").read(4) == b"IxFI"
+    flat = faiss.read_index(fpath)
+    assert isinstance(flat, faiss.IndexFlatIP) and flat.ntotal == 3000
+    np.testing.assert_array_equal(flat.reconstruct_n(0, 3000), xb)
+    D2, I2 = flat.search(xq, 21)
+    assert (I0 == I2).all() and (D0 == D2).all()
+    half = faiss.read_index(fpath, storage="f16")
+    assert half.storage == "f16" and half.ntotal == 3000
+    # a k-means-partitioned file as the reference's build-index.py writes it (nlist 100, ids scattered
+    # over the lists) flattens back into add order
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_faiss_io import ivf_bytes
+    assign = np.random.default_rng(0).integers(0, 100, size=3000)
+    kpath = str(tmp_path / "kmeans.index")
+    open(kpath, "wb").write(ivf_bytes(xb, assign, 100, 32))
+    km = faiss.read_index(kpath)
+    assert isinstance(km, faiss.IndexIVFFlat) and km.nlist == 100 and km.nprobe == 32
+    D3, I3 = km.search(xq, 21)
+    assert (I0 == I3).all() and (D0 == D3).all()
     # fp16 storage rounds rows exactly like numpy
     h = faiss.IndexFlatIP(512, storage="f16")
     h.add(xb)
