@@ -92,6 +92,11 @@ struct cb_clip {
     bool lanes_ready = false;
     int next_lane = 0;
     cudaEvent_t fence_ev = nullptr;
+    // CUDA graphs of small forward passes (<= kGraphMaxBatch rows): a single query is ~70 tiny launches,
+    // i.e. launch-bound; the replay costs one launch.  Keyed by (entry point, batch, normalize).
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; bool seen = false, failed = false; };
+    std::map<int, GraphEntry> graphs;
+    float *d_img_f32 = nullptr;     // fixed input slot of the fp32-image graphs (allocated on first use)
     // live GEMM timing (bench.py roofline)
     int timing = 0;                 // 0 off, 1 GEMM launches only, 2 every kernel class
     std::vector<cudaEvent_t> ev;
@@ -348,6 +353,56 @@ int text_forward(cb_clip *m, Ws &w, int B, const int32_t *ids_dev, float *out_de
     return CB_OK;
 }
 
+constexpr int kGraphMaxBatch = 32;
+
+void drop_graphs(cb_clip *m) {
+    for (auto &kv : m->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    m->graphs.clear();
+}
+
+// Run `body(in, out, stream)` - one small forward pass - as a CUDA graph replay.
+// The graph is captured once per (kind, b, normalize) on the handle's own stream with FIXED
+// buffers (`slot_in` -> workspace -> m->d_out); a replay on the caller's stream is
+//   copy in_dev -> slot_in (skipped when the caller already passed the slot), graph launch,
+//   copy m->d_out -> out_dev.
+// The first call of a key runs the plain launches (it also sets the kernels' attributes); timing
+// mode and CLIPB200_NO_GRAPH=1 always do.  A failed capture falls back to plain launches for good.
+template <typename Body>
+int graphed_forward(cb_clip *m, int kind, int b, int normalize, const void *in_dev, void *slot_in, size_t in_bytes,
+                    float *out_dev, cudaStream_t s, Body &&body) {
+    static const bool off = getenv("CLIPB200_NO_GRAPH") && atoi(getenv("CLIPB200_NO_GRAPH"));
+    if (off || m->timing || b > kGraphMaxBatch) return body(in_dev, out_dev, s);
+    cb_clip::GraphEntry &e = m->graphs[(kind << 16) | (b << 1) | (normalize ? 1 : 0)];
+    if (!e.seen || e.failed) {
+        e.seen = true;
+        return body(in_dev, out_dev, s);
+    }
+    if (!e.exec) {
+        const int64_t before = g_launches;
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = ce == cudaSuccess ? body(slot_in, m->d_out, m->stream) : CB_ERR_CUDA;
+        if (ce == cudaSuccess) ce = cudaStreamEndCapture(m->stream, &graph);
+        if (rc == CB_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        e.launches = (int)(g_launches - before);
+        g_launches = before;                       // a capture launches nothing
+        if (rc != CB_OK || ce != cudaSuccess || !e.exec) {
+            cudaGetLastError();
+            e.exec = nullptr;
+            e.failed = true;
+            return body(in_dev, out_dev, s);
+        }
+    }
+    if (in_dev != slot_in) CB_CUDA(cudaMemcpyAsync(slot_in, in_dev, in_bytes, cudaMemcpyDeviceToDevice, s));
+    CB_CUDA(cudaGraphLaunch(e.exec, s));
+    g_launches += e.launches;
+    if (out_dev != m->d_out)
+        CB_CUDA(cudaMemcpyAsync(out_dev, m->d_out, (size_t)b * ED * 4, cudaMemcpyDeviceToDevice, s));
+    return CB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -391,9 +446,10 @@ void cb_clip_free(cb_clip *m) {
     if (!m) return;
     DeviceGuard g(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    drop_graphs(m);
     for (auto &kv : m->params) cudaFree(kv.second.dev);
     free_ws(m->ws);
-    void *bufs[] = {m->d_img, m->d_ids, m->d_out, m->cls_pos};
+    void *bufs[] = {m->d_img, m->d_ids, m->d_out, m->cls_pos, m->d_img_f32};
     for (void *p : bufs) cudaFree(p);
     for (cudaEvent_t ev : m->ev) cudaEventDestroy(ev);
     for (Lane &l : m->lanes) {
@@ -451,6 +507,7 @@ int cb_clip_set_param(cb_clip *m, const char *name_c, const float *host, int64_t
 int cb_clip_finalize(cb_clip *m) {
     CB_REQUIRE(m != nullptr, "cb_clip_finalize: null handle");
     DeviceGuard g(m->device);
+    drop_graphs(m);                 // captured graphs hold the old parameter pointers
     int rc = 0;
     const float *cls_emb = nullptr;
     rc |= need(m, "visual.conv1.weight", 768ll * 3072, true, &m->conv1_w);
@@ -500,7 +557,11 @@ int cb_clip_encode_image_u8_device(cb_clip *m, int64_t B, const uint8_t *hwc_dev
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t lo = 0; lo < B; lo += m->max_img) {
         const int b = (int)std::min<int64_t>(m->max_img, B - lo);
-        int rc = encode_u8_chunk(m, m->ws, b, hwc_dev + (size_t)lo * 224 * 224 * 3, out_dev + lo * ED, normalize, s);
+        const size_t in_bytes = (size_t)b * 224 * 224 * 3;
+        int rc = graphed_forward(m, 0, b, normalize, hwc_dev + (size_t)lo * 224 * 224 * 3, m->d_img, in_bytes,
+                                 out_dev + lo * ED, s, [&](const void *in, float *out, cudaStream_t cs) {
+                                     return encode_u8_chunk(m, m->ws, b, (const uint8_t *)in, out, normalize, cs);
+                                 });
         if (rc) return rc;
     }
     return CB_OK;
@@ -517,9 +578,15 @@ int cb_clip_encode_image_f32_device(cb_clip *m, int64_t B, const float *nchw_dev
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t lo = 0; lo < B; lo += m->max_img) {
         const int b = (int)std::min<int64_t>(m->max_img, B - lo);
-        int rc = preprocess_f32(nchw_dev + (size_t)lo * 3 * 224 * 224, m->ws.patches, b, s);
+        const size_t in_bytes = (size_t)b * 3 * 224 * 224 * 4;
+        if (b <= kGraphMaxBatch && !m->d_img_f32)
+            CB_CUDA(cudaMalloc(&m->d_img_f32, (size_t)std::min(kGraphMaxBatch, m->max_img) * 3 * 224 * 224 * 4));
+        int rc = graphed_forward(m, 1, b, normalize, nchw_dev + (size_t)lo * 3 * 224 * 224, m->d_img_f32, in_bytes,
+                                 out_dev + lo * ED, s, [&](const void *in, float *out, cudaStream_t cs) {
+                                     int r = preprocess_f32((const float *)in, m->ws.patches, b, cs);
+                                     return r ? r : vision_from_patches(m, m->ws, b, out, normalize, cs);
+                                 });
         if (rc) return rc;
-        if ((rc = vision_from_patches(m, m->ws, b, out_dev + lo * ED, normalize, s))) return rc;
     }
     return CB_OK;
 }
@@ -535,7 +602,10 @@ int cb_clip_encode_text_device(cb_clip *m, int64_t B, const int32_t *ids_dev, fl
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t lo = 0; lo < B; lo += m->max_txt) {
         const int b = (int)std::min<int64_t>(m->max_txt, B - lo);
-        int rc = text_forward(m, m->ws, b, ids_dev + lo * TL, out_dev + lo * ED, normalize, s);
+        int rc = graphed_forward(m, 2, b, normalize, ids_dev + lo * TL, m->d_ids, (size_t)b * TL * 4, out_dev + lo * ED, s,
+                                 [&](const void *in, float *out, cudaStream_t cs) {
+                                     return text_forward(m, m->ws, b, (const int32_t *)in, out, normalize, cs);
+                                 });
         if (rc) return rc;
     }
     return CB_OK;

@@ -178,6 +178,53 @@ def test_batch_chunking_and_batch_invariance(model, sd):
     assert _cos(torch, solo, all_[20:21]) >= 0.99999
 
 
+def test_small_batches_replay_cuda_graphs(sd, golden_inputs):
+    """Forward passes of <= 32 rows are captured into a CUDA graph on their second call and replayed
+    from then on (a single query is launch-bound).  Replays must equal the plain launches bit for
+    bit, follow their inputs, and still be counted as kernel launches."""
+    import torch
+    from clipb200 import _native as N, clip
+    from oracle import clip_ref
+    images, tokens, _ = golden_inputs
+    m = clip.CLIPB200(sd, device=0, max_image_batch=8, max_text_batch=8)
+    imgs = images.cuda()
+    toks = tokens.cuda()
+    f32 = clip_ref.preprocess_u8(images).cuda()
+    for enc, a, b in ((lambda x: m.encode_image(x, normalize=True), imgs[0:1], imgs[1:2]),
+                      (lambda x: m.encode_image(x, normalize=True), f32[0:1], f32[2:3]),
+                      (lambda x: m.encode_text(x, normalize=True), toks[0:1], toks[3:4]),
+                      (lambda x: m.encode_text(x), toks[0:3], toks[1:4])):
+        N.launch_count(reset=True)
+        plain = enc(a).clone()                       # first call of this shape: plain launches
+        n_plain = N.launch_count(reset=True)
+        first = enc(a).clone()                       # second call: capture + replay
+        n_replay = N.launch_count(reset=True)
+        again = enc(a).clone()                       # pure replay
+        other = enc(b).clone()                       # replay with different input
+        back = enc(a).clone()
+        torch.cuda.synchronize()
+        assert n_plain >= 60 and n_replay == n_plain, (n_plain, n_replay)
+        assert torch.equal(plain, first) and torch.equal(plain, again) and torch.equal(plain, back)
+        assert not torch.equal(plain, other)
+    # the replayed single-row results are the rows of the batched result (different GEMM tiles: tolerance)
+    full = m.encode_image(imgs, normalize=True)
+    one = m.encode_image(imgs[1:2], normalize=True)
+    assert _cos(torch, one, full[1:2]) >= 0.99999
+    # host entry points replay too and agree with the device entry points
+    h1 = m.encode_text_host(tokens[0:1].numpy(), normalize=True)
+    h2 = m.encode_text_host(tokens[0:1].numpy(), normalize=True)
+    d = m.encode_text(toks[0:1], normalize=True).cpu().numpy()
+    assert np.array_equal(h1, h2) and np.array_equal(h1, d)
+    # re-finalising (new parameters) drops the graphs: results follow the new weights
+    before = m.encode_text(toks[0:1], normalize=True).clone()
+    sd2 = dict(sd)
+    sd2["text_projection"] = sd["text_projection"] * 0.5 + 0.01
+    m2 = clip.CLIPB200(sd2, device=0, max_image_batch=0, max_text_batch=8)
+    for _ in range(3):
+        after = m2.encode_text(toks[0:1], normalize=True)
+    assert not torch.equal(before, after)
+
+
 def test_host_entry_points_equal_device_entry_points(model, golden_inputs):
     import torch
     images, tokens, _ = golden_inputs
