@@ -37,7 +37,14 @@ constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant, each owns half of the tile's columns
 constexpr int kThreads = 64 + kEpiWarps * 32;
 
-template <int BN, int NCTA>
+// staging boxes per epilogue warp: the bias / bias+GELU epilogues stream their 32-column chunks through a
+// ring of kRingBoxes (the bulk store of a box overlaps the next chunk's math), which leaves room
+// for one or two more pipeline stages; the residual and patch epilogues need all chunks resident
+constexpr int kRingBoxes = 2;
+template <int EPI>
+__host__ __device__ constexpr bool kRingEpi() { return EPI == EPI_BIAS || EPI == EPI_BIAS_GELU; }
+
+template <int BN, int NCTA, int EPI>
 struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_ROWS = BN / NCTA;                  // rows of W this CTA loads per k-block
@@ -50,7 +57,8 @@ struct Cfg {
     // for both row-per-thread and row-contiguous accesses), followed by the warp's BN/2 fp32 bias
     static constexpr int EPI_COLS = BN / 2;
     static constexpr int EPI_BOX_BYTES = 32 * 64;
-    static constexpr int EPI_BIAS_OFF = (EPI_COLS / 32) * EPI_BOX_BYTES;
+    static constexpr int NBOX = kRingEpi<EPI>() && EPI_COLS / 32 > kRingBoxes ? kRingBoxes : EPI_COLS / 32;
+    static constexpr int EPI_BIAS_OFF = NBOX * EPI_BOX_BYTES;
     static constexpr int EPI_WARP_BYTES = EPI_BIAS_OFF + 2 * EPI_COLS * 4;   // + bias and colsum slices
     static constexpr int kMaxSmem = 232448;                   // 227 KB opt-in limit
     static constexpr int FIXED = BAR_BYTES + kEpiWarps * EPI_WARP_BYTES + 1024 + 1024;   // + alignment slack
@@ -83,7 +91,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     };
     // m_tiles counts (128*NCTA)-row tiles; a cluster of NCTA CTAs owns one tile at a time
-    using C = Cfg<BN, NCTA>;
+    using C = Cfg<BN, NCTA, EPI>;
     const uint32_t cta_rank = NCTA == 1 ? 0u : cluster_ctarank();
     const bool leader = cta_rank == 0;
     const int cluster_id = blockIdx.x / NCTA, num_clusters = gridDim.x / NCTA;
@@ -140,7 +148,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                         tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
                         tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN, &full[stage]);
-                    } else if (dbg_mode == 3 && tile != cluster_id) {
+                    } else if ((dbg_mode == 3 || dbg_mode == 5) && tile != cluster_id) {
                         // experiment: traffic of a W-stationary schedule (W loaded for the first tile only;
                         // results are garbage)
                         if (leader) mbar_expect_tx(&full[stage], NCTA * C::A_BYTES);
@@ -192,15 +200,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         constexpr bool kTmaStore = EPI != EPI_F32 && EPI != EPI_PATCH;
         // staging area starts 1024-byte aligned (TMA + swizzle pattern alignment)
         const uint32_t stage_area = (smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + 1023u) & ~1023u;
-        const uint32_t stage_base = stage_area + (uint32_t)(warp - 2) * C::EPI_BOX_BYTES * (EC / 32);
-        const uint32_t bias_smem = stage_area + kEpiWarps * C::EPI_BOX_BYTES * (EC / 32) + (uint32_t)(warp - 2) * EC * 8;
+        constexpr int NBOX = C::NBOX;
+        const uint32_t stage_base = stage_area + (uint32_t)(warp - 2) * C::EPI_BOX_BYTES * NBOX;
+        const uint32_t bias_smem = stage_area + kEpiWarps * C::EPI_BOX_BYTES * NBOX + (uint32_t)(warp - 2) * EC * 8;
         const uint32_t csum_smem = bias_smem + EC * 4;
         const bool ln_fold = kHasBiasT<EPI>() && g.ln_stats != nullptr;
         const bool emit_stats = EPI == EPI_BIAS_RESID && g.stats_out != nullptr;
         const int out_slices = g.N / EC;
         // 16-byte chunk j (of this warp's EC columns) of row r: box j/4, 64-byte rows, 64B swizzle
         auto stg = [&](int r, int j) -> uint32_t {
-            return stage_base + (uint32_t)(j >> 2) * C::EPI_BOX_BYTES + (uint32_t)r * 64u +
+            return stage_base + (uint32_t)((j >> 2) % NBOX) * C::EPI_BOX_BYTES + (uint32_t)r * 64u +
                    (uint32_t)((((j & 3) ^ ((r >> 1) & 3))) << 4);
         };
         constexpr bool kHasBias = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID;
@@ -254,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             if (EPI == EPI_BIAS_RESID) cp_async_wait_all();
             __syncwarp();
-            if (dbg_mode == 1) {      // experiment: MMA-only throughput (results are not written)
+            if (dbg_mode == 1 || dbg_mode == 5) {      // experiment: MMA-only throughput (results are not written)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -275,7 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (kTmaStore && EPI != EPI_BIAS_RESID) {
                     // box c is rewritten below: its bulk store of the previous tile (one group per box, so
                     // NB - 1 younger groups may still be pending) must have finished reading it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(EC / 32 - 1) : "memory");
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBOX - 1) : "memory");
                     __syncwarp();
                 }
                 uint32_t v[32];
@@ -374,7 +383,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         __syncwarp();
                         if (lane == 0) {
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                         ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(stage_base + c * C::EPI_BOX_BYTES),
+                                         ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(stage_base + (c % NBOX) * C::EPI_BOX_BYTES),
                                            "r"(n0), "r"(row0)
                                          : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -473,7 +482,7 @@ int make_out_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols,
 
 template <int BN, int EPI, int NCTA>
 int launch(const GemmArgs &g, cudaStream_t s) {
-    using C = Cfg<BN, NCTA>;
+    using C = Cfg<BN, NCTA, EPI>;
     auto kern = gemm_tcgen05_kernel<BN, EPI, NCTA>;
     int cur_dev = 0;
     CB_CUDA(cudaGetDevice(&cur_dev));

@@ -4,6 +4,7 @@
   mainloop  CLIPB200_GEMM_DEBUG=1: TMA + MMA only (epilogue warps just release the accumulator)
   A-only    CLIPB200_GEMM_DEBUG=3: full kernel, but W tiles are loaded for a cluster's first tile only (the
             operand traffic a W-stationary schedule would have; results are garbage)
+  A-only+mainloop  CLIPB200_GEMM_DEBUG=5: both of the above (is the mainloop bound by operand delivery?)
   cublas    torch's fp16 matmul (cuBLASLt) on the same operands, bias/activation/residual NOT included
 CUDA events, 30 launches each after 5 warm-ups."""
 import ctypes as C
@@ -49,7 +50,7 @@ for (M, Nn, K, epi, name) in SHAPES:
 
     fl = 2 * M * Nn * K / 1e9
     line = f"{name:16s} M={M} N={Nn} K={K} epi={epi}:"
-    for label, dbg in (("full", None), ("nostore", "2"), ("mainloop", "1"), ("A-only", "3")):
+    for label, dbg in (("full", None), ("nostore", "2"), ("mainloop", "1"), ("A-only", "3"), ("A-only+mainloop", "5")):
         if dbg is None:
             os.environ.pop("CLIPB200_GEMM_DEBUG", None)
         else:
