@@ -309,14 +309,21 @@ class Searcher:
         with self.env.begin(db=self.fn_db) as txn:
             return np.frombuffer(txn.get(key), dtype=np.float32).reshape((1, 512))
 
+    def path_for_id(self, image_id: int) -> str:
+        with self.env.begin(db=self.idx_db) as txn:
+            return txn.get(f"{image_id}".encode()).decode()
+
     def results(self, features: np.ndarray, k: int = 50, offset: int = 0) -> List[Tuple[float, int, str]]:
-        """Rows the REPL prints: search k+offset+1, skip ranks j <= offset (query-index.py:111-119)."""
+        """Rows the REPL prints: search k+offset+1, skip ranks j <= offset (query-index.py:111-119).
+        Stops at the -1 padding when fewer rows exist than were asked for."""
         D, I = self.index.search(features, k + offset + 1)
         rows = []
         with self.env.begin(db=self.idx_db) as txn:
             for j, i in enumerate(I[0]):
                 if j <= offset:
                     continue
+                if i < 0:
+                    break
                 rows.append((float(D[0][j]), int(i), txn.get(f"{i}".encode()).decode()))
         return rows
 

@@ -126,3 +126,71 @@ def test_gpu_resize_and_nvjpeg_paths(tmp_path, monkeypatch):
     for k in stores["cpu"]:
         assert np.array_equal(stores["cpu"][k], stores["gpu"][k]), k
         assert float((stores["cpu"][k] * stores["nvjpeg"][k]).sum()) >= 0.999, k
+
+
+def test_query_session_commands_and_quirks(tmp_path, monkeypatch):
+    """The query loop (query-index.py:40-119) as a state machine: same lines out for the same lines
+    in, with encode_text and index.search on the GPU."""
+    import re
+    from clipb200 import clip, faiss, indexer, lmdb, repl, weights
+    from oracle import clip_ref
+
+    folder = str(tmp_path / "photos") + "/"
+    _make_folder(folder, n=30)
+    monkeypatch.chdir(tmp_path)
+    model = clip.CLIPB200(weights.synthetic_state_dict(0), device=0, max_image_batch=32, max_text_batch=4)
+    env = lmdb.open("vectors.lmdb", map_size=1 << 30, max_dbs=4)
+    indexer.embed_folders([folder], env, model, batch=32, out=io.StringIO())
+    indexer.build_index(env, faiss, index_path="images.index", out=io.StringIO())
+    index = faiss.read_index("images.index")           # as query-index.py:29-30
+    index.nprobe = 32
+
+    class SyntheticTextSearcher(indexer.Searcher):     # no BPE vocabulary offline: text -> seeded token row
+        def features_for_text(self, text):
+            return self.features_for_tokens(clip_ref.synthetic_tokens(1, seed=len(text)))
+
+    lines = []
+    s = repl.QuerySession(SyntheticTextSearcher(env, index, model), index, out=lines.append)
+
+    def feed(text):
+        lines.clear()
+        alive = s.handle(text)
+        return alive, list(lines)
+
+    assert repl.PROMPT == "[h,q,i,r,a,c,p] >>> "
+    assert feed("h")[1][0].startswith("Enter a search query")
+    assert feed("")[1] == []                                   # "more" before any text query: nothing
+    assert feed("p 100")[1] == ["Set to probe 100 subsets."] and index.nprobe == 100
+    assert feed("p 101")[1] == ["Invalid probe value."] and feed("p 0")[1] == ["Invalid probe value."]
+    assert feed("c 5")[1] == ["Showing 5 results."]
+    assert feed("c 0")[1] == ["Reset number of results to 50."] and s.k == 50
+    assert feed("r 1280x720")[1] == ["Set maximum resolution to 1280x720."] and s.max_res == (1280, 720)
+    assert feed("r nonsense")[1] == ["Unset maximum resolution."] and s.max_res is None
+    assert feed("a")[1] == ["Aligning window position."] and feed("a")[1] == ["Not aligning window position."]
+    feed("c 5")
+
+    alive, out = feed("a photo of a dog")
+    assert alive and re.fullmatch(r"Search time: \d+\.\d{4}s", out[0]) and len(out) == 6
+    first = [re.fullmatch(r"(-?\d+\.\d{4}) (\d+) (.+)", l).groups() for l in out[1:]]
+    D, I = index.search(s.features, 11)
+    assert [int(f[1]) for f in first] == list(I[0][1:6])       # rank 0 skipped, k + offset + 1 requested
+    assert all(f[2].startswith(folder) for f in first) and s.last_j == 5
+    _, out = feed("")                                          # more: ranks 6..10
+    assert [int(l.split(" ")[1]) for l in out[1:]] == list(I[0][6:11]) and s.last_j == 10
+
+    _, out = feed("i 7")                                       # similar to a stored image
+    assert out[0].startswith("Similar to " + folder) and out[0].endswith(":")
+    assert len(out) == 7 and int(out[2].split(" ")[1]) != 7    # rank 0 (the image itself) is skipped
+    D7, I7 = index.search(s.features, 6)
+    assert I7[0][0] == 7 and [int(l.split(" ")[1]) for l in out[2:]] == list(I7[0][1:6])
+    assert feed("i 9999")[1] == ["Not found."]
+
+    feed("c 100")                                              # more than the index holds: stops at the last row
+    _, out = feed("another query")
+    assert len(out) == 1 + 29
+    shown = []
+    s.show = lambda path, sess: (shown.append(path), len(shown) < 3)[1]   # viewer says "q" on the 3rd image
+    _, out = feed("third")
+    assert len(shown) == 3 and len(out) == 1 + 3 and s.last_j == 3
+    assert feed("q")[0] is False
+    env.close()
