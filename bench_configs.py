@@ -3,9 +3,10 @@
 single-query half of configs[2]).  One JSON line per config; same timing hygiene as bench.py
 (warm-up, CUDA events on the launching stream, max over ranks, inputs larger than L2).
 
-  python bench_configs.py [--configs 3,4,5] [--rows-per-gpu N]
+  python bench_configs.py [--configs 1,3,4,5] [--rows-per-gpu N]
   torchrun --nproc-per-node 8 bench_configs.py --configs 3,5
 
+  configs[0] (--configs 1) build-index over 1,000 synthetic JPEG files + one text query, end to end from disk
   configs[2] exact IP search over 10M x 512 fp16 sharded over the GPUs, k=100:
              single-query latency (p50/p99 per query) and batch-1024 throughput
   configs[3] image-similarity query: encode_image of one query image + top-100 over 10M
@@ -80,10 +81,95 @@ def per_call_ms(fn, n, warm):
     return out
 
 
+def make_jpeg_folder(root, n, seed=1234):
+    """low-frequency random field + N(0, 8) noise, 224 x 224 RGB, JPEG quality 90."""
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    os.makedirs(root, exist_ok=True)
+    for i in range(n):
+        base = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+        im = np.asarray(Image.fromarray(base).resize((224, 224), Image.BICUBIC), dtype=np.float32)
+        arr = np.clip(im + rng.normal(0, 8, im.shape), 0, 255).astype(np.uint8)
+        Image.fromarray(arr).save(os.path.join(root, f"img_{i:06d}.jpg"), quality=90)
+
+
+def run_config0(emit, n_images=1000):
+    """BASELINE configs[0]: build-index over 1,000 synthetic 224px JPEGs + one text query top-20, end to
+    end from files on disk (decode included), one GPU; the reference's own loop (PIL transform, one
+    image per forward pass, fp32 CPU oracle) on a bounded sample of the same files beside it."""
+    import io
+    import shutil
+    import tempfile
+    from PIL import Image
+    from clipb200 import clip, faiss, indexer, lmdb, weights
+    from oracle import clip_ref, flatip_ref
+    tmp = tempfile.mkdtemp(prefix="clipb200_cfg0_")
+    cwd = os.getcwd()
+    try:
+        folder = os.path.join(tmp, "photos") + "/"
+        make_jpeg_folder(folder, n_images)
+        sd = weights.synthetic_state_dict(0)
+        model = clip.CLIPB200(sd, device=torch.cuda.current_device(), max_image_batch=256, max_text_batch=1)
+        tokens = clip_ref.synthetic_tokens(1, seed=4)
+        res = {}
+        for mode, kw in (("pil_threads", {}), ("nvjpeg", {"decode": "nvjpeg"})):
+            work = os.path.join(tmp, mode)
+            os.makedirs(work)
+            os.chdir(work)
+            # warm-up pass on a few files (kernel attributes, pinned buffers, nvjpeg handle)
+            wenv = lmdb.open("warm.lmdb", map_size=1 << 30, max_dbs=4)
+            wf = os.path.join(tmp, "warm_" + mode) + "/"
+            os.makedirs(wf)
+            for fn in sorted(os.listdir(folder))[:64]:
+                shutil.copy(folder + fn, wf + fn)
+            try:
+                indexer.embed_folders([wf], wenv, model, out=io.StringIO(), **kw)
+            except Exception as e:        # e.g. torchvision built without nvjpeg
+                res[mode] = {"unavailable": str(e)[:200]}
+                wenv.close()
+                continue
+            wenv.close()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            env = lmdb.open("vectors.lmdb", map_size=1 << 30, max_dbs=4)
+            ok, bad = indexer.embed_folders([folder], env, model, out=io.StringIO(), **kw)
+            t_embed = time.perf_counter() - t0
+            index = indexer.build_index(env, faiss, index_path="images.index", out=io.StringIO())
+            t_index = time.perf_counter() - t0 - t_embed
+            searcher = indexer.Searcher(env, index, model)
+            tq = time.perf_counter()
+            rows = searcher.results(searcher.features_for_tokens(tokens), k=20, offset=0)
+            t_query = time.perf_counter() - tq
+            res[mode] = {"embedded": ok, "failed": bad, "embed_s": t_embed, "images_per_s": ok / t_embed,
+                         "build_index_s": t_index, "text_query_top20_ms": t_query * 1e3, "top1_id": rows[0][1]}
+            env.close()
+        os.chdir(cwd)
+        # the reference's loop on the host cores: transform + encode_image one image at a time
+        torch.set_num_threads(os.cpu_count() or 1)
+        transform = clip._transform(224)
+        files = sorted(os.listdir(folder))
+        n, t0, feats = 0, time.perf_counter(), []
+        while n < len(files) and time.perf_counter() - t0 < 15.0:
+            x = transform(Image.open(folder + files[n])).unsqueeze(0)
+            feats.append(clip_ref.l2_normalize_rows(clip_ref.encode_image(sd, x)))
+            n += 1
+        dt = time.perf_counter() - t0
+        emit({"config": f"configs[0]: build-index over {n_images:,} synthetic 224px JPEGs + text query top-20 (files on "
+                        "disk -> vectors.lmdb + images.index -> result rows)",
+              "clipb200": res,
+              "cpu_reference_loop": {"images_per_s": n / dt, "images": n, "seconds": dt, "cores": os.cpu_count(),
+                                     "kind": "port", "what": "PIL transform + oracle/clip_ref.py fp32 encode_image, one "
+                                     "image per forward pass as at build-index.py:48-51"}})
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="3,4,5")
     ap.add_argument("--rows-per-gpu", type=int, default=None)
+    ap.add_argument("--images", type=int, default=1000, help="files in the configs[0] folder")
     args = ap.parse_args()
     want = {int(c) for c in args.configs.split(",")}
     rank, world, local = dist_env()
@@ -99,6 +185,9 @@ def main():
         if rank == 0:
             d.update({"n_gpus": world, "data": "synthetic"})
             print(json.dumps(d), flush=True)
+
+    if 1 in want and rank == 0:
+        run_config0(emit, args.images)
 
     if want & {3, 4}:
         N = 10_000_000

@@ -150,6 +150,71 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
     return n_ok, n_bad
 
 
+def _nvjpeg_chunks(todo: List[str], chunk: int, pool: ThreadPoolExecutor, dev, threads: Optional[int] = None):
+    """Yield (names, items) per chunk of files, in order, decoded up to 2 x `threads` chunks ahead of the
+    consumer by `threads` worker threads (CLIPB200_NVJPEG_THREADS, default 2).  torchvision serialises its
+    nvjpeg calls (~0.18 ms per 224 px image, measured), so more threads only overlap the file reads.  A JPEG item is
+    the decoded CHW uint8 CUDA tensor of one batched nvjpeg call per chunk (torchvision: a list
+    decodes far faster than one call per file); if the batched call fails - one corrupt file fails
+    the whole list - the chunk is decoded file by file so only the bad ones are lost.  Other
+    formats come back as the decoded array of the CPU path.  A failed file is None."""
+    import torchvision.io as tvio
+    from concurrent.futures import ThreadPoolExecutor as _TPE
+
+    read_op = torch.ops.image.read_file             # the op itself: tvio.read_file adds ~0.1 ms of API logging
+
+    def read_jpeg(tfn: str):
+        try:
+            return read_op(tfn)                     # uint8 tensor straight from the file, no Python copy
+        except Exception:
+            return None
+
+    def prepare(names: List[str]):
+        items: List = [None] * len(names)
+        jidx, jten = [], []
+        is_jpeg = [tfn.lower().endswith((".jpg", ".jpeg")) for tfn in names]
+        raw = list(pool.map(lambda a: read_jpeg(a[0]) if a[1] else None, zip(names, is_jpeg)))
+        for i, tfn in enumerate(names):
+            if is_jpeg[i]:
+                t = raw[i]
+                if t is not None and t.numel() > 0:
+                    jidx.append(i)
+                    jten.append(t)
+            else:
+                items[i] = _decode_full(tfn)
+        if jten:
+            with torch.cuda.device(dev):
+                try:
+                    dec = tvio.decode_jpeg(jten, device=dev, mode=tvio.ImageReadMode.RGB)
+                except Exception:
+                    dec = []
+                    for t in jten:
+                        try:
+                            dec.append(tvio.decode_jpeg(t, device=dev, mode=tvio.ImageReadMode.RGB))
+                        except Exception:
+                            dec.append(None)
+            for i, d in zip(jidx, dec):
+                items[i] = d
+            # the common case - every file of the chunk decoded to 224 x 224 - travels as ONE [m,3,224,224]
+            # tensor, so the consumer places it with one strided copy instead of one launch per image
+            if len(jidx) == len(names) and all(d is not None and tuple(d.shape) == (3, 224, 224) for d in dec):
+                with torch.cuda.device(dev):
+                    return names, torch.stack(dec)
+        return names, items
+
+    threads = threads or int(os.environ.get("CLIPB200_NVJPEG_THREADS", "2"))
+    chunk = max(16, min(chunk, 64))
+    chunks = [todo[i:i + chunk] for i in range(0, len(todo), chunk)]
+    with _TPE(max_workers=threads) as stage:
+        pending = []
+        for c in chunks:
+            pending.append(stage.submit(prepare, c))
+            if len(pending) > 2 * threads:
+                yield pending.pop(0).result()
+        for f in pending:
+            yield f.result()
+
+
 def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) -> Tuple[int, int]:
     import ctypes as C
     from . import _native as N
@@ -164,8 +229,6 @@ def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) 
     dbuf = [torch.empty((batch, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     dout = [torch.empty((batch, 512), dtype=torch.float32, device=dev) for _ in range(nbuf)]
     use_nvjpeg = decode == "nvjpeg"
-    if use_nvjpeg:
-        import torchvision.io as tvio
 
     def commit(names, vecs):
         nonlocal n_ok
@@ -177,17 +240,11 @@ def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) 
 
     def to_device_224(item, tfn, dst):
         """item: raw file bytes (nvjpeg) or a decoded array.  Writes [224,224,3] into dst."""
-        if use_nvjpeg and isinstance(item, (bytes, bytearray)):
-            low = tfn.lower()
-            if low.endswith((".jpg", ".jpeg")):
-                data = torch.frombuffer(bytearray(item), dtype=torch.uint8)
-                chw = tvio.decode_jpeg(data, device=dev, mode=tvio.ImageReadMode.RGB)
-                src = chw.permute(1, 2, 0).contiguous()
-            else:
-                px = _decode_full(tfn)
-                if px is None:
-                    return False
-                src = torch.from_numpy(px).to(dev, non_blocking=True)
+        if torch.is_tensor(item):                       # nvjpeg output: CHW uint8 on the device
+            if tuple(item.shape) == (3, 224, 224):
+                dst.copy_(item.permute(1, 2, 0))
+                return True
+            src = item.permute(1, 2, 0).contiguous()
         else:
             src = torch.from_numpy(item).to(dev, non_blocking=True)
         if tuple(src.shape) == (224, 224, 3):
@@ -230,8 +287,24 @@ def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) 
                 slot = (slot + 1) % nbuf
                 names, fill = [], 0
 
-            loader = _read_bytes if use_nvjpeg else _decode_full
-            for tfn, item in zip(todo, pool.map(loader, todo)):
+            def nvjpeg_items():
+                nonlocal names, fill
+                for names_, items_ in _nvjpeg_chunks(todo, batch, pool, dev):
+                    if not torch.is_tensor(items_):
+                        yield from zip(names_, items_)
+                        continue
+                    a = 0                                   # whole chunk as one NCHW tensor: bulk placement
+                    while a < len(names_):
+                        take = min(batch - fill, len(names_) - a)
+                        dbuf[slot][fill:fill + take].copy_(items_[a:a + take].permute(0, 2, 3, 1))
+                        names.extend(names_[a:a + take])
+                        fill += take
+                        a += take
+                        if fill == batch:
+                            flush()
+
+            stream_items = nvjpeg_items() if use_nvjpeg else zip(todo, pool.map(_decode_full, todo))
+            for tfn, item in stream_items:
                 ok = False
                 if item is not None:
                     try:
