@@ -70,6 +70,11 @@ SIGNATURES = {
     "cb_preprocess_f32_device": (_int, [_p, _p, _int, _p]),
     "cb_l2norm_f32_device": (_int, [_p, _p, _int, _int, _p]),
     "cb_resize224_u8_device": (_int, [_p, _int, _int, _p, _p]),
+    "cb_jpeg_create": (_int, [_int, _int, C.POINTER(_p)]),
+    "cb_jpeg_free": (None, [_p]),
+    "cb_jpeg_threads": (_int, [_p]),
+    "cb_jpeg_decode_files": (_int, [_p, _i64, C.POINTER(C.c_char_p), _p, _p]),
+    "cb_jpeg_decode_memory": (_int, [_p, _i64, C.POINTER(_p), C.POINTER(_i64), _p, _p]),
     "cb_gemm_f16_ex_device": (_int, [_int, _int, _int, _p, _p, _p, _p, _p, _int, _p, _int, _p, _p, _p]),
     "cb_gemm_out_slices": (_int, [_int, _int]),
     "cb_gemm_f16_device": (_int, [_int, _int, _int, _p, _p, _p, _p, _p, _p, _int, _int, _p]),

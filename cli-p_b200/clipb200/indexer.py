@@ -76,8 +76,9 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
 
     resize="cpu": Pillow resizes (exactly the reference's transform); resize="gpu": full-resolution
     RGB pixels are uploaded and resized by cb_resize224_u8_device (bit-identical to Pillow).
-    decode="nvjpeg" (implies resize="gpu"): JPEG files are decoded on the GPU by nvjpeg through
-    torchvision (library work; pixels may differ from libjpeg-turbo by +-1)."""
+    decode="nvjpeg" (implies resize="gpu"): JPEG files are read and decoded a batch per call by
+    clipb200.jpeg.Decoder (host threads + nvjpeg behind the C ABI; library work for the decode itself,
+    pixels may differ from libjpeg-turbo by +-1); other formats still go through Pillow."""
     if decode == "nvjpeg" or resize == "gpu":
         return _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode)
     fn_db = env.open_db(b"fn_db")
@@ -150,69 +151,52 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
     return n_ok, n_bad
 
 
-def _nvjpeg_chunks(todo: List[str], chunk: int, pool: ThreadPoolExecutor, dev, threads: Optional[int] = None):
-    """Yield (names, items) per chunk of files, in order, decoded up to 2 x `threads` chunks ahead of the
-    consumer by `threads` worker threads (CLIPB200_NVJPEG_THREADS, default 2).  torchvision serialises its
-    nvjpeg calls (~0.18 ms per 224 px image, measured), so more threads only overlap the file reads.  A JPEG item is
-    the decoded CHW uint8 CUDA tensor of one batched nvjpeg call per chunk (torchvision: a list
-    decodes far faster than one call per file); if the batched call fails - one corrupt file fails
-    the whole list - the chunk is decoded file by file so only the bad ones are lost.  Other
-    formats come back as the decoded array of the CPU path.  A failed file is None."""
-    import torchvision.io as tvio
-    from concurrent.futures import ThreadPoolExecutor as _TPE
+def _nvjpeg_chunks(todo: List[str], chunk: int, decoder, dev, depth: int = 1):
+    """Yield (names, pixels, status) per chunk of files, in order, decoded `depth` chunks ahead of the
+    consumer.  JPEG files of a chunk are decoded by ONE call into the C ABI (clipb200.jpeg.Decoder:
+    host threads + nvjpeg, no Python in the loop) into a rotating [chunk,224,224,3] device buffer;
+    status[i] is 0 for a decoded file, -1 for a file that is not a JPEG (the caller decodes it on the
+    CPU), anything else for a failure (see clipb200/jpeg.py)."""
+    stages = [torch.empty((chunk, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(depth + 2)]
+    # the consumer records `released[b]` once its copies out of stages[b] are queued; the decoder (which
+    # writes on its own streams) waits for that before it overwrites the buffer
+    released: List[Optional[torch.cuda.Event]] = [None] * len(stages)
 
-    read_op = torch.ops.image.read_file             # the op itself: tvio.read_file adds ~0.1 ms of API logging
+    def prepare(k: int, names: List[str]):
+        jidx = [i for i, tfn in enumerate(names) if tfn.lower().endswith((".jpg", ".jpeg"))]
+        status = np.full(len(names), -1, dtype=np.int32)
+        b = k % len(stages)
+        px = stages[b]
+        if released[b] is not None:
+            released[b].synchronize()
+        if jidx:
+            if len(jidx) == len(names):
+                _, st = decoder.decode_files(names, out=px)
+                status[:] = st
+            else:                                   # mixed chunk: decode the JPEGs to the front, note where they go
+                tmp, st = decoder.decode_files([names[i] for i in jidx])
+                px[torch.as_tensor(jidx, device=dev)] = tmp
+                status[jidx] = st
+        return names, px, status, b
 
-    def read_jpeg(tfn: str):
-        try:
-            return read_op(tfn)                     # uint8 tensor straight from the file, no Python copy
-        except Exception:
-            return None
+    def release(b: int):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        released[b] = ev
 
-    def prepare(names: List[str]):
-        items: List = [None] * len(names)
-        jidx, jten = [], []
-        is_jpeg = [tfn.lower().endswith((".jpg", ".jpeg")) for tfn in names]
-        raw = list(pool.map(lambda a: read_jpeg(a[0]) if a[1] else None, zip(names, is_jpeg)))
-        for i, tfn in enumerate(names):
-            if is_jpeg[i]:
-                t = raw[i]
-                if t is not None and t.numel() > 0:
-                    jidx.append(i)
-                    jten.append(t)
-            else:
-                items[i] = _decode_full(tfn)
-        if jten:
-            with torch.cuda.device(dev):
-                try:
-                    dec = tvio.decode_jpeg(jten, device=dev, mode=tvio.ImageReadMode.RGB)
-                except Exception:
-                    dec = []
-                    for t in jten:
-                        try:
-                            dec.append(tvio.decode_jpeg(t, device=dev, mode=tvio.ImageReadMode.RGB))
-                        except Exception:
-                            dec.append(None)
-            for i, d in zip(jidx, dec):
-                items[i] = d
-            # the common case - every file of the chunk decoded to 224 x 224 - travels as ONE [m,3,224,224]
-            # tensor, so the consumer places it with one strided copy instead of one launch per image
-            if len(jidx) == len(names) and all(d is not None and tuple(d.shape) == (3, 224, 224) for d in dec):
-                with torch.cuda.device(dev):
-                    return names, torch.stack(dec)
-        return names, items
-
-    threads = threads or int(os.environ.get("CLIPB200_NVJPEG_THREADS", "2"))
-    chunk = max(16, min(chunk, 64))
     chunks = [todo[i:i + chunk] for i in range(0, len(todo), chunk)]
-    with _TPE(max_workers=threads) as stage:
+    with ThreadPoolExecutor(max_workers=1) as stage:
         pending = []
-        for c in chunks:
-            pending.append(stage.submit(prepare, c))
-            if len(pending) > 2 * threads:
-                yield pending.pop(0).result()
+        for k, c in enumerate(chunks):
+            pending.append(stage.submit(prepare, k, c))
+            if len(pending) > depth:
+                names, px, status, b = pending.pop(0).result()
+                yield names, px, status
+                release(b)
         for f in pending:
-            yield f.result()
+            names, px, status, b = f.result()
+            yield names, px, status
+            release(b)
 
 
 def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) -> Tuple[int, int]:
@@ -229,6 +213,11 @@ def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) 
     dbuf = [torch.empty((batch, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     dout = [torch.empty((batch, 512), dtype=torch.float32, device=dev) for _ in range(nbuf)]
     use_nvjpeg = decode == "nvjpeg"
+    decoder = None
+    if use_nvjpeg:
+        from . import jpeg
+        decoder = jpeg.Decoder(dev.index if isinstance(dev, torch.device) else int(dev),
+                               int(os.environ.get("CLIPB200_NVJPEG_THREADS", "0")))
 
     def commit(names, vecs):
         nonlocal n_ok
@@ -288,20 +277,27 @@ def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) 
                 names, fill = [], 0
 
             def nvjpeg_items():
-                nonlocal names, fill
-                for names_, items_ in _nvjpeg_chunks(todo, batch, pool, dev):
-                    if not torch.is_tensor(items_):
-                        yield from zip(names_, items_)
-                        continue
-                    a = 0                                   # whole chunk as one NCHW tensor: bulk placement
-                    while a < len(names_):
-                        take = min(batch - fill, len(names_) - a)
-                        dbuf[slot][fill:fill + take].copy_(items_[a:a + take].permute(0, 2, 3, 1))
-                        names.extend(names_[a:a + take])
+                nonlocal names, fill, n_bad
+                for names_, px, status in _nvjpeg_chunks(todo, batch, decoder, dev):
+                    good = np.nonzero(status == 0)[0]
+                    a = 0                                   # decoded rows: bulk placement, one gather per batch slot
+                    while a < len(good):
+                        take = min(batch - fill, len(good) - a)
+                        sel = good[a:a + take]
+                        if take == len(names_):
+                            dbuf[slot][fill:fill + take].copy_(px[:take])
+                        else:
+                            dbuf[slot][fill:fill + take] = px[torch.as_tensor(sel, device=dev)]
+                        names.extend(names_[i] for i in sel)
                         fill += take
                         a += take
                         if fill == batch:
                             flush()
+                    for i in np.nonzero(status != 0)[0]:
+                        if status[i] in (-1, 4):            # not a JPEG / not supported by nvjpeg: CPU decode
+                            yield names_[i], _decode_full(names_[i])
+                        else:
+                            yield names_[i], None
 
             stream_items = nvjpeg_items() if use_nvjpeg else zip(todo, pool.map(_decode_full, todo))
             for tfn, item in stream_items:

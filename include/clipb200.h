@@ -190,6 +190,26 @@ int cb_l2norm_f32_device(const float *in, float *out, int rows, int width, void 
 int cb_resize224_u8_device(const uint8_t *src_hwc, int h, int w, uint8_t *dst_224x224x3,
                            void *stream);
 
+/* ---- JPEG files -> pixel batches in HBM (index-time caller of path A) -------
+ * Image.open(tfn) + transform(image)                      build-index.py:47-48
+ * for a whole batch of files in one call: `threads` host threads (0 = one per
+ * core, at most 16), each with its own nvjpeg decoder state and CUDA stream,
+ * read + entropy-decode the files and the GPU finishes them as interleaved RGB
+ * straight into out_dev[i] (uint8 [224][224][3]); images of another size go
+ * through cb_resize224_u8_device first.  nvjpeg is library code, loaded with
+ * dlopen; pixels may differ from libjpeg-turbo's by +-1.
+ * status[i]: 0 ok, 1 file unreadable, 2 not a decodable JPEG, 3 CUDA error,
+ * 4 unsupported here (the caller decodes that file on the CPU instead).
+ * The call returns when every out_dev[i] with status 0 is complete. */
+typedef struct cb_jpeg cb_jpeg;
+int cb_jpeg_create(int device, int threads, cb_jpeg **out);
+void cb_jpeg_free(cb_jpeg *j);
+int cb_jpeg_threads(const cb_jpeg *j);
+int cb_jpeg_decode_files(cb_jpeg *j, int64_t n, const char *const *paths, uint8_t *out_dev,
+                         int32_t *status);
+int cb_jpeg_decode_memory(cb_jpeg *j, int64_t n, const uint8_t *const *data, const int64_t *sizes,
+                          uint8_t *out_dev, int32_t *status);
+
 /* ---- tcgen05 GEMM building block (exported for unit tests and benches) ----
  * C[M,N] = epilogue(A[M,K] fp16 row-major x W[N,K]^T fp16 row-major), fp32
  * accumulation in tensor memory.  Replaces the cuBLAS calls torch dispatches for
