@@ -739,9 +739,11 @@ int cb_flatip_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_
         return CB_OK;
     }
     // query batches: tensor-core GEMM + fused threshold filter (fp16 shards, k <= 1024).
-    // Below ~16 queries the HBM-bound streaming scan is faster (crossover
-    // where 2 x 256-query MMA work costs more than re-streaming the shard per 4 queries).
-    int64_t batch_min = 16;
+    // The GEMM pass costs ~3.3 ms over 10M rows whatever nq <= 256 is (one 256-query tile column); the
+    // streaming scan costs 1.5 ms for one query, 2.9 ms for four and another pass per four after that,
+    // so the crossover is at five queries (profiles/r01_batch_crossover.txt).  Small shards keep the old
+    // threshold: there both paths are bounded by their launch counts, not by the pass over the rows.
+    int64_t batch_min = ix->ntotal >= (1ll << 20) ? 5 : 16;
     if (const char *e = getenv("CLIPB200_BATCH_MIN_NQ")) batch_min = atoll(e);
     if (nq >= batch_min && ix->dtype == CB_F16 && k <= 1024 && ix->ntotal >= 8192) {
         if (!ix->bws) ix->bws = batch_ws_new();
