@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 template <int L, bool CAUSAL>
-__global__ void __launch_bounds__(((L + 15) / 16) * 32)
+__global__ void __launch_bounds__(((L + 15) / 16) * 32, L <= 64 ? 8 : 6)
 attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int heads) {
     constexpr int KT = (L + 15) / 16;   // 16-key steps (= 16-row query tiles = warps)
     constexpr int LP = KT * 16;         // padded sequence
@@ -54,16 +54,24 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
     const int W = heads * HD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // stage q|k|v of this head: 3 x LP rows x 8 chunks of 16 B, global -> shared with cp.async
-    // (no register round trip); rows >= L are zero
-    for (int i = threadIdx.x; i < 3 * LP * 8; i += blockDim.x) {
-        const int ch = i & 7, row = (i >> 3) % LP, mat = i / (8 * LP);
-        __half *dst = (mat == 0 ? sQ : (mat == 1 ? sK : sV)) + row * LDS + ch * 8;
-        if (row < L) {
-            const __half *src = qkv + ((size_t)(b * L + row) * 3 + mat) * W + h * HD + ch * 8;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-        } else if (mat == 2) {
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+    // stage q|k|v of this head: 3 x LP rows x 8 chunks of 16 B, global -> shared with cp.async (no register
+    // round trip); rows >= L of V are zero.  blockDim = 8 chunks x (4 KT) rows, so iteration `it` of the
+    // fully unrolled loop covers rows (it & 3) * 4 KT .. of matrix it >> 2: no index arithmetic per chunk
+    {
+        const int r8 = threadIdx.x >> 3, ch = threadIdx.x & 7;
+        const __half *src0 = qkv + ((size_t)(b * L + r8) * 3) * W + h * HD + ch * 8;
+        __half *dst0 = sbuf + r8 * LDS + ch * 8;
+#pragma unroll
+        for (int it = 0; it < 12; it++) {
+            const int mat = it >> 2, rb = (it & 3) * (KT * 4);        // compile-time after unrolling
+            const int row = r8 + rb;
+            __half *dst = dst0 + ((mat == 0 ? 0 : (mat == 1 ? L : 2 * L)) + rb) * LDS;
+            if (row < L) {
+                const __half *src = src0 + ((size_t)rb * 3 + mat) * W;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+            } else if (mat == 2) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+            }
         }
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -112,7 +120,8 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
     for (int nt = 0; nt < NT; nt++) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            const float p = exp2f(s[nt][e] - (e < 2 ? m0 : m1));   // exp2(-inf) = 0 for masked keys
+            float p;                                               // ex2.approx(-inf) = 0 for masked keys
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(s[nt][e] - (e < 2 ? m0 : m1)));
             s[nt][e] = p;
             if (e < 2) sum0 += p; else sum1 += p;
         }
