@@ -108,7 +108,7 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
             const int key = nt * 8 + (lane & 3) * 2 + (e & 1);
             const int row = e < 2 ? r0 : r1;
             const bool masked = key >= L || (CAUSAL && key > row);
-            const float v = masked ? -INFINITY : s[nt][e] * sl2;
+            const float v = masked ? -INFINITY : s[nt][e];        // raw score; the scale rides in the FMA below
             s[nt][e] = v;
             if (e < 2) m0 = fmaxf(m0, v); else m1 = fmaxf(m1, v);
         }
@@ -116,12 +116,13 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float sum0 = 0.f, sum1 = 0.f;
+    const float c0 = -m0 * sl2, c1 = -m1 * sl2;                   // every row has an unmasked key: m is finite
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             float p;                                               // ex2.approx(-inf) = 0 for masked keys
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(s[nt][e] - (e < 2 ? m0 : m1)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[nt][e], sl2, e < 2 ? c0 : c1)));
             s[nt][e] = p;
             if (e < 2) sum0 += p; else sum1 += p;
         }
