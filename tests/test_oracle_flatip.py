@@ -109,3 +109,18 @@ def test_tolerance_rule():
     I = np.array([[1, 2, 3, 4]])
     assert F.ids_match_with_tolerance(D, I, D, np.array([[1, 3, 2, 4]]))[0]
     assert not F.ids_match_with_tolerance(D, I, D, np.array([[2, 1, 3, 4]]))[0]
+
+
+def test_numpy_oracle_matches_scikit_learn_brute_force():
+    """A third, independent exact k-NN: scikit-learn's brute-force neighbours under the cosine metric.
+    On unit-norm rows cosine distance = 1 - <q, x>, so its neighbour order is the inner-product order."""
+    from sklearn.neighbors import NearestNeighbors
+    xb = synth.unit_rows(20_000, seed=11, clip_like=True)
+    xq = synth.unit_rows(8, seed=12, clip_like=True)
+    for k in (1, 21, 100):
+        D, I = F.search(xq, xb, k)
+        nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="cosine").fit(xb)
+        dist, idx = nn.kneighbors(xq)
+        ok, _, msg = F.ids_match_with_tolerance(D, I, (1.0 - dist).astype(np.float32), idx.astype(np.int64))
+        assert ok, msg
+        np.testing.assert_allclose(D, 1.0 - dist, atol=2e-6)
