@@ -175,6 +175,7 @@ void free_worker(cb_jpeg *j, Worker &w) {
 
 template <typename GetData>
 int decode_batch(cb_jpeg *j, int64_t n, uint8_t *out_dev, int32_t *status, GetData &&get) {
+    DeviceGuard guard(j->device);          // worker 0 is the calling thread: leave its current device as it was
     std::atomic<int64_t> next(0);
     const int nt = (int)std::min<int64_t>((int64_t)j->workers.size(), n);
     auto body = [&](int t) {
