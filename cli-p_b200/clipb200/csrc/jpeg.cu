@@ -75,9 +75,16 @@ int load_api(NvjApi **out) {
 constexpr int OUT = 224;
 constexpr size_t OUT_BYTES = (size_t)OUT * OUT * 3;
 
+// Two nvjpeg back ends per worker, picked per image by its pixel count (profiles/r01_jpeg_sizes.txt):
+// [0] NVJPEG_BACKEND_HYBRID      Huffman decoding on the worker's host core: 55 k images/s at 224 px on 16
+//                                threads, but 377/s at 12 Mpixel
+// [1] NVJPEG_BACKEND_GPU_HYBRID  Huffman decoding on the GPU: 940 images/s (11 Gpixel/s) at 12 Mpixel, but
+//                                4x slower than [0] on thumbnails
+constexpr int64_t kGpuHuffmanMinPixels = 4 << 20;
+
 struct Worker {
-    nvjpegJpegDecoder_t decoder = nullptr;
-    nvjpegJpegState_t state = nullptr;
+    nvjpegJpegDecoder_t decoder[2] = {nullptr, nullptr};
+    nvjpegJpegState_t state[2] = {nullptr, nullptr};
     nvjpegBufferPinned_t pinned = nullptr;
     nvjpegBufferDevice_t devbuf = nullptr;
     nvjpegJpegStream_t jstream = nullptr;
@@ -96,7 +103,7 @@ struct cb_jpeg {
     cb::NvjApi *api = nullptr;
     nvjpegHandle_t handle = nullptr;
     std::vector<cb::Worker> workers;
-    std::mutex resize_mu;              // the resize weight-table cache is not thread safe
+    int force_backend = -1;            // CLIPB200_NVJPEG_BACKEND=1|2 pins one back end (experiments)
 };
 
 using namespace cb;
@@ -127,18 +134,25 @@ int decode_one(cb_jpeg *j, Worker &w, const uint8_t *data, size_t len, uint8_t *
     nvjpegImage_t img = {};
     img.channel[0] = target;
     img.pitch[0] = (size_t)W * 3;
-    nvjpegStatus_t st = a.nvjpegDecodeJpegHost(j->handle, w.decoder, w.state, w.params, w.jstream);
-    if (st == NVJPEG_STATUS_SUCCESS) st = a.nvjpegDecodeJpegTransferToDevice(j->handle, w.decoder, w.state, w.jstream, w.stream);
-    if (st == NVJPEG_STATUS_SUCCESS) st = a.nvjpegDecodeJpegDevice(j->handle, w.decoder, w.state, &img, w.stream);
+    int be = (int64_t)W * H >= kGpuHuffmanMinPixels ? 1 : 0;
+    if (j->force_backend >= 0) be = j->force_backend;
+    if (!w.decoder[be]) be ^= 1;
+    nvjpegStatus_t st = a.nvjpegDecodeJpegHost(j->handle, w.decoder[be], w.state[be], w.params, w.jstream);
+    if (st == NVJPEG_STATUS_SUCCESS) st = a.nvjpegDecodeJpegTransferToDevice(j->handle, w.decoder[be], w.state[be], w.jstream, w.stream);
+    if (st == NVJPEG_STATUS_SUCCESS) st = a.nvjpegDecodeJpegDevice(j->handle, w.decoder[be], w.state[be], &img, w.stream);
+    if (st != NVJPEG_STATUS_SUCCESS && be == 1 && w.decoder[0]) {
+        // the GPU Huffman decoder takes baseline files only: progressive and the like go to the host decoder
+        cudaStreamSynchronize(w.stream);
+        st = a.nvjpegDecodeJpegHost(j->handle, w.decoder[0], w.state[0], w.params, w.jstream);
+        if (st == NVJPEG_STATUS_SUCCESS) st = a.nvjpegDecodeJpegTransferToDevice(j->handle, w.decoder[0], w.state[0], w.jstream, w.stream);
+        if (st == NVJPEG_STATUS_SUCCESS) st = a.nvjpegDecodeJpegDevice(j->handle, w.decoder[0], w.state[0], &img, w.stream);
+    }
     if (st != NVJPEG_STATUS_SUCCESS) {
         cudaStreamSynchronize(w.stream);
         return st == NVJPEG_STATUS_JPEG_NOT_SUPPORTED ? 4 : 2;
     }
     int rc = 0;
-    if (!direct) {
-        std::lock_guard<std::mutex> lk(j->resize_mu);
-        if (cb_resize224_u8_device(target, (int)H, (int)W, dst, w.stream) != CB_OK) rc = 3;
-    }
+    if (!direct && cb_resize224_u8_device(target, (int)H, (int)W, dst, w.stream) != CB_OK) rc = 3;
     // the pinned/device buffers of this worker and its scratch image are reused by its next file
     if (cudaStreamSynchronize(w.stream) != cudaSuccess) { cudaGetLastError(); rc = 3; }
     return rc;
@@ -164,10 +178,12 @@ void free_worker(cb_jpeg *j, Worker &w) {
     if (w.stream) cudaStreamSynchronize(w.stream);
     if (w.params) a.nvjpegDecodeParamsDestroy(w.params);
     if (w.jstream) a.nvjpegJpegStreamDestroy(w.jstream);
-    if (w.state) a.nvjpegJpegStateDestroy(w.state);
+    for (int b = 0; b < 2; b++)
+        if (w.state[b]) a.nvjpegJpegStateDestroy(w.state[b]);
     if (w.devbuf) a.nvjpegBufferDeviceDestroy(w.devbuf);
     if (w.pinned) a.nvjpegBufferPinnedDestroy(w.pinned);
-    if (w.decoder) a.nvjpegDecoderDestroy(w.decoder);
+    for (int b = 0; b < 2; b++)
+        if (w.decoder[b]) a.nvjpegDecoderDestroy(w.decoder[b]);
     if (w.scratch) cudaFree(w.scratch);
     if (w.stream) cudaStreamDestroy(w.stream);
     w = Worker();
@@ -222,18 +238,29 @@ int cb_jpeg_create(int device, int threads, cb_jpeg **out) {
     j->device = device;
     j->api = api;
     bool ok = api->nvjpegCreateSimple(&j->handle) == NVJPEG_STATUS_SUCCESS;
-    // Huffman decoding on the host cores (one file per thread); CLIPB200_NVJPEG_BACKEND=2 selects the
-    // GPU-assisted Huffman decoder, which pays off for multi-megapixel files
-    int backend = NVJPEG_BACKEND_HYBRID;
-    if (const char *e = getenv("CLIPB200_NVJPEG_BACKEND")) backend = atoi(e);
+    if (const char *e = getenv("CLIPB200_NVJPEG_BACKEND")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2) j->force_backend = v - 1;
+    }
     j->workers.resize(ok ? threads : 0);
     for (Worker &w : j->workers) {
-        ok = ok && api->nvjpegDecoderCreate(j->handle, (nvjpegBackend_t)backend, &w.decoder) == NVJPEG_STATUS_SUCCESS;
-        ok = ok && api->nvjpegDecoderStateCreate(j->handle, w.decoder, &w.state) == NVJPEG_STATUS_SUCCESS;
         ok = ok && api->nvjpegBufferPinnedCreate(j->handle, nullptr, &w.pinned) == NVJPEG_STATUS_SUCCESS;
         ok = ok && api->nvjpegBufferDeviceCreate(j->handle, nullptr, &w.devbuf) == NVJPEG_STATUS_SUCCESS;
-        ok = ok && api->nvjpegStateAttachPinnedBuffer(w.state, w.pinned) == NVJPEG_STATUS_SUCCESS;
-        ok = ok && api->nvjpegStateAttachDeviceBuffer(w.state, w.devbuf) == NVJPEG_STATUS_SUCCESS;
+        const nvjpegBackend_t kinds[2] = {NVJPEG_BACKEND_HYBRID, NVJPEG_BACKEND_GPU_HYBRID};
+        for (int b = 0; b < 2 && ok; b++) {
+            // the GPU Huffman back end is optional (the host one decodes everything); both share the buffers
+            bool got = api->nvjpegDecoderCreate(j->handle, kinds[b], &w.decoder[b]) == NVJPEG_STATUS_SUCCESS &&
+                       api->nvjpegDecoderStateCreate(j->handle, w.decoder[b], &w.state[b]) == NVJPEG_STATUS_SUCCESS &&
+                       api->nvjpegStateAttachPinnedBuffer(w.state[b], w.pinned) == NVJPEG_STATUS_SUCCESS &&
+                       api->nvjpegStateAttachDeviceBuffer(w.state[b], w.devbuf) == NVJPEG_STATUS_SUCCESS;
+            if (!got && b == 0) ok = false;
+            if (!got && b == 1) {
+                if (w.state[1]) api->nvjpegJpegStateDestroy(w.state[1]);
+                if (w.decoder[1]) api->nvjpegDecoderDestroy(w.decoder[1]);
+                w.state[1] = nullptr;
+                w.decoder[1] = nullptr;
+            }
+        }
         ok = ok && api->nvjpegJpegStreamCreate(j->handle, &w.jstream) == NVJPEG_STATUS_SUCCESS;
         ok = ok && api->nvjpegDecodeParamsCreate(j->handle, &w.params) == NVJPEG_STATUS_SUCCESS;
         ok = ok && api->nvjpegDecodeParamsSetOutputFormat(w.params, NVJPEG_OUTPUT_RGBI) == NVJPEG_STATUS_SUCCESS;
