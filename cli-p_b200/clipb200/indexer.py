@@ -73,13 +73,15 @@ def _read_bytes(tfn: str):
 def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers: Optional[int] = None,
                   out=sys.stdout, resize: str = "cpu", decode: str = "pil") -> Tuple[int, int]:
     """Embed every new image under `folders` into fn_db.  Returns (embedded, failed).
+    `model` may be a list of CLIPB200 handles, one per GPU: the files are then split over the devices
+    (GPU decode/resize path), each device runs independently and this thread commits to LMDB.
 
     resize="cpu": Pillow resizes (exactly the reference's transform); resize="gpu": full-resolution
     RGB pixels are uploaded and resized by cb_resize224_u8_device (bit-identical to Pillow).
     decode="nvjpeg" (implies resize="gpu"): JPEG files are read and decoded a batch per call by
     clipb200.jpeg.Decoder (host threads + nvjpeg behind the C ABI; library work for the decode itself,
     pixels may differ from libjpeg-turbo by +-1); other formats still go through Pillow."""
-    if decode == "nvjpeg" or resize == "gpu":
+    if decode == "nvjpeg" or resize == "gpu" or isinstance(model, (list, tuple)):
         return _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode)
     fn_db = env.open_db(b"fn_db")
     skip_db = env.open_db(b"skip_db")
@@ -199,25 +201,114 @@ def _nvjpeg_chunks(todo: List[str], chunk: int, decoder, dev, depth: int = 1):
             release(b)
 
 
-def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) -> Tuple[int, int]:
+def _device_pipeline(todo: List[str], model, batch: int, workers: int, decode: str, on_done, on_bad) -> None:
+    """Embed `todo` on model.device: decode (nvjpeg through the C ABI, or Pillow in a thread pool) and
+    resize on the GPU, batches of `batch` through the two-lane submit API.  Calls on_done(names, vecs)
+    (vecs: float32 CPU tensor [n,512], L2-normalised) per finished batch and on_bad(name) per failed file,
+    from the calling thread.  One call per device; several may run in parallel threads."""
     import ctypes as C
     from . import _native as N
     L = N.lib()
+    dev = model.device
+    nbuf = 3
+    use_nvjpeg = decode == "nvjpeg"
+    with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=workers) as pool:
+        dbuf = [torch.empty((batch, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        dout = [torch.empty((batch, 512), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+        decoder = None
+        if use_nvjpeg:
+            from . import jpeg
+            decoder = jpeg.Decoder(dev.index, int(os.environ.get("CLIPB200_NVJPEG_THREADS", "0")))
+
+        def to_device_224(item, dst):
+            """item: a decoded uint8 array [h,w,3].  Writes [224,224,3] into dst."""
+            src = torch.from_numpy(item).to(dev, non_blocking=True)
+            if tuple(src.shape) == (224, 224, 3):
+                dst.copy_(src)
+            else:
+                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                N.check(L.cb_resize224_u8_device(C.c_void_p(src.data_ptr()), src.shape[0], src.shape[1],
+                                                 C.c_void_p(dst.data_ptr()), stream))
+                src.record_stream(torch.cuda.current_stream(dev))
+
+        inflight = []
+        slot, names, fill = 0, [], 0
+
+        def drain():
+            N.check(L.cb_clip_join(model.handle, model._stream()))
+            for s_, nm_, n_ in inflight:
+                on_done(nm_, dout[s_][:n_].cpu())
+            inflight.clear()
+
+        def flush():
+            nonlocal slot, names, fill
+            if fill == 0:
+                return
+            N.check(L.cb_clip_submit_image_u8_device(model.handle, fill, C.c_void_p(dbuf[slot].data_ptr()),
+                                                     C.c_void_p(dout[slot].data_ptr()), 1, model._stream()))
+            inflight.append((slot, names, fill))
+            if len(inflight) >= nbuf - 1:
+                drain()
+            slot = (slot + 1) % nbuf
+            names, fill = [], 0
+
+        def nvjpeg_items():
+            nonlocal names, fill
+            for names_, px, status in _nvjpeg_chunks(todo, batch, decoder, dev):
+                good = np.nonzero(status == 0)[0]
+                a = 0                                   # decoded rows: bulk placement, one gather per batch slot
+                while a < len(good):
+                    take = min(batch - fill, len(good) - a)
+                    sel = good[a:a + take]
+                    if take == len(names_):
+                        dbuf[slot][fill:fill + take].copy_(px[:take])
+                    else:
+                        dbuf[slot][fill:fill + take] = px[torch.as_tensor(sel, device=dev)]
+                    names.extend(names_[i] for i in sel)
+                    fill += take
+                    a += take
+                    if fill == batch:
+                        flush()
+                for i in np.nonzero(status != 0)[0]:
+                    if status[i] in (-1, 4):            # not a JPEG / not supported by nvjpeg: CPU decode
+                        yield names_[i], _decode_full(names_[i])
+                    else:
+                        yield names_[i], None
+
+        stream_items = nvjpeg_items() if use_nvjpeg else zip(todo, pool.map(_decode_full, todo))
+        for tfn, item in stream_items:
+            ok = False
+            if item is not None:
+                try:
+                    to_device_224(item, dbuf[slot][fill])
+                    ok = True
+                except KeyboardInterrupt:
+                    raise
+                except Exception:
+                    ok = False
+            if not ok:
+                on_bad(tfn)
+                continue
+            names.append(tfn)
+            fill += 1
+            if fill == batch:
+                flush()
+        flush()
+        drain()
+
+
+def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) -> Tuple[int, int]:
+    """GPU decode/resize driver.  `model` is one CLIPB200 or a list of them, one per device (SURVEY.md 8e:
+    the files of a folder are split contiguously over the devices, each device runs its own pipeline in a
+    thread with no collective, and this thread - the only LMDB writer - commits what they finish)."""
+    import queue
+    import threading
+    models = list(model) if isinstance(model, (list, tuple)) else [model]
     fn_db = env.open_db(b"fn_db")
     skip_db = env.open_db(b"skip_db")
-    batch = min(batch, model.max_image_batch)
-    workers = workers or min(32, os.cpu_count() or 4)
-    dev = model.device
+    batch = min([batch] + [m.max_image_batch for m in models])
+    workers = workers or max(2, min(32, os.cpu_count() or 4) // len(models))
     n_ok = n_bad = 0
-    nbuf = 3
-    dbuf = [torch.empty((batch, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-    dout = [torch.empty((batch, 512), dtype=torch.float32, device=dev) for _ in range(nbuf)]
-    use_nvjpeg = decode == "nvjpeg"
-    decoder = None
-    if use_nvjpeg:
-        from . import jpeg
-        decoder = jpeg.Decoder(dev.index if isinstance(dev, torch.device) else int(dev),
-                               int(os.environ.get("CLIPB200_NVJPEG_THREADS", "0")))
 
     def commit(names, vecs):
         nonlocal n_ok
@@ -227,99 +318,54 @@ def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) 
                 print(".", end="", flush=True, file=out)
                 n_ok += 1
 
-    def to_device_224(item, tfn, dst):
-        """item: raw file bytes (nvjpeg) or a decoded array.  Writes [224,224,3] into dst."""
-        if torch.is_tensor(item):                       # nvjpeg output: CHW uint8 on the device
-            if tuple(item.shape) == (3, 224, 224):
-                dst.copy_(item.permute(1, 2, 0))
-                return True
-            src = item.permute(1, 2, 0).contiguous()
-        else:
-            src = torch.from_numpy(item).to(dev, non_blocking=True)
-        if tuple(src.shape) == (224, 224, 3):
-            dst.copy_(src)
-        else:
-            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            N.check(L.cb_resize224_u8_device(C.c_void_p(src.data_ptr()), src.shape[0], src.shape[1],
-                                             C.c_void_p(dst.data_ptr()), stream))
-            src.record_stream(torch.cuda.current_stream(dev))
-        return True
+    def bad(name):
+        nonlocal n_bad
+        print("#", end="", flush=True, file=out)
+        n_bad += 1
 
-    with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=workers) as pool:
-        for base_path in folders:
-            print(f"CLIPing {base_path}...", file=out)
-            todo = []
-            with env.begin(db=skip_db) as st, env.begin(db=fn_db) as ft:
-                for tfn in list_images(base_path):
-                    key = tfn.encode()
-                    if len(key) > 511 or st.get(key) is not None or ft.get(key) is not None:
-                        continue
-                    todo.append(tfn)
-            inflight = []
-            slot, names, fill = 0, [], 0
-
-            def drain():
-                N.check(L.cb_clip_join(model.handle, model._stream()))
-                for s_, nm_, n_ in inflight:
-                    commit(nm_, dout[s_][:n_].cpu())
-                inflight.clear()
-
-            def flush():
-                nonlocal slot, names, fill
-                if fill == 0:
-                    return
-                N.check(L.cb_clip_submit_image_u8_device(model.handle, fill, C.c_void_p(dbuf[slot].data_ptr()),
-                                                         C.c_void_p(dout[slot].data_ptr()), 1, model._stream()))
-                inflight.append((slot, names, fill))
-                if len(inflight) >= nbuf - 1:
-                    drain()
-                slot = (slot + 1) % nbuf
-                names, fill = [], 0
-
-            def nvjpeg_items():
-                nonlocal names, fill, n_bad
-                for names_, px, status in _nvjpeg_chunks(todo, batch, decoder, dev):
-                    good = np.nonzero(status == 0)[0]
-                    a = 0                                   # decoded rows: bulk placement, one gather per batch slot
-                    while a < len(good):
-                        take = min(batch - fill, len(good) - a)
-                        sel = good[a:a + take]
-                        if take == len(names_):
-                            dbuf[slot][fill:fill + take].copy_(px[:take])
-                        else:
-                            dbuf[slot][fill:fill + take] = px[torch.as_tensor(sel, device=dev)]
-                        names.extend(names_[i] for i in sel)
-                        fill += take
-                        a += take
-                        if fill == batch:
-                            flush()
-                    for i in np.nonzero(status != 0)[0]:
-                        if status[i] in (-1, 4):            # not a JPEG / not supported by nvjpeg: CPU decode
-                            yield names_[i], _decode_full(names_[i])
-                        else:
-                            yield names_[i], None
-
-            stream_items = nvjpeg_items() if use_nvjpeg else zip(todo, pool.map(_decode_full, todo))
-            for tfn, item in stream_items:
-                ok = False
-                if item is not None:
-                    try:
-                        ok = to_device_224(item, tfn, dbuf[slot][fill])
-                    except KeyboardInterrupt:
-                        raise
-                    except Exception:
-                        ok = False
-                if not ok:
-                    print("#", end="", flush=True, file=out)
-                    n_bad += 1
+    for base_path in folders:
+        print(f"CLIPing {base_path}...", file=out)
+        todo = []
+        with env.begin(db=skip_db) as st, env.begin(db=fn_db) as ft:
+            for tfn in list_images(base_path):
+                key = tfn.encode()
+                if len(key) > 511 or st.get(key) is not None or ft.get(key) is not None:
                     continue
-                names.append(tfn)
-                fill += 1
-                if fill == batch:
-                    flush()
-            flush()
-            drain()
-            print(flush=True, file=out)
+                todo.append(tfn)
+        if len(models) == 1:
+            _device_pipeline(todo, models[0], batch, workers, decode, commit, bad)
+        else:
+            R = len(models)
+            per = -(-len(todo) // R) if todo else 0
+            events: "queue.Queue" = queue.Queue(maxsize=4 * R)
+            errors: List[BaseException] = []
+
+            def run(r):
+                try:
+                    _device_pipeline(todo[r * per:(r + 1) * per], models[r], batch, workers, decode,
+                                     lambda nm, v: events.put(("ok", nm, v)), lambda nm: events.put(("bad", nm, None)))
+                except BaseException as e:      # surfaced in the committing thread
+                    errors.append(e)
+                finally:
+                    events.put(("end", None, None))
+
+            threads = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(R)]
+            for t in threads:
+                t.start()
+            live = R
+            while live:
+                kind, nm, v = events.get()
+                if kind == "ok":
+                    commit(nm, v)
+                elif kind == "bad":
+                    bad(nm)
+                else:
+                    live -= 1
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+        print(flush=True, file=out)
     return n_ok, n_bad
 
 

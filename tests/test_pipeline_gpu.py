@@ -194,3 +194,35 @@ def test_query_session_commands_and_quirks(tmp_path, monkeypatch):
     assert len(shown) == 3 and len(out) == 1 + 3 and s.last_j == 3
     assert feed("q")[0] is False
     env.close()
+
+
+def test_two_gpus_embed_one_folder(tmp_path, monkeypatch):
+    """SURVEY.md 8e, index time: the files of a folder are split over the GPUs (one replica each, no
+    collective), one thread commits.  The stored vectors are those of the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    from clipb200 import clip, indexer, lmdb, weights
+    folder = str(tmp_path / "photos") + "/"
+    _make_folder(folder, n=300)
+    monkeypatch.chdir(tmp_path)
+    sd = weights.synthetic_state_dict(0)
+    stores = []
+    for name, models in (("one", None), ("two", [0, 1])):
+        if models is None:
+            m = clip.CLIPB200(sd, device=0, max_image_batch=64, max_text_batch=1)
+        else:
+            m = [clip.CLIPB200(sd, device=d, max_image_batch=64, max_text_batch=1) for d in models]
+        env = lmdb.open(f"{name}.lmdb", map_size=1 << 30, max_dbs=4)
+        log = io.StringIO()
+        ok, bad = indexer.embed_folders([folder], env, m, batch=64, out=log, decode="nvjpeg")
+        marks = log.getvalue().split("\n", 1)[1]           # progress characters after the "CLIPing ..." line
+        assert (ok, bad) == (300, 1) and marks.count(".") == 300 and marks.count("#") == 1
+        with env.begin(db=env.open_db(b"fn_db")) as txn:
+            stores.append({k: bytes(v) for k, v in txn.cursor()})
+        env.close()
+    assert stores[0].keys() == stores[1].keys() and len(stores[0]) == 300
+    a = np.stack([np.frombuffer(stores[0][k], dtype=np.float32) for k in sorted(stores[0])])
+    b = np.stack([np.frombuffer(stores[1][k], dtype=np.float32) for k in sorted(stores[0])])
+    # same decoder, same kernels, but a row's batch neighbours differ (tile shapes) -> fp16-level differences
+    assert (a * b).sum(1).min() >= 0.99999
