@@ -112,7 +112,7 @@ def run_config0(emit, n_images=1000):
         model = clip.CLIPB200(sd, device=torch.cuda.current_device(), max_image_batch=256, max_text_batch=1)
         tokens = clip_ref.synthetic_tokens(1, seed=4)
         res = {}
-        for mode, kw in (("pil_threads", {}), ("nvjpeg", {"decode": "nvjpeg"})):
+        for mode, kw in (("pillow", {}), ("nvjpeg", {"decode": "nvjpeg"})):
             work = os.path.join(tmp, mode)
             os.makedirs(work)
             os.chdir(work)

@@ -162,22 +162,7 @@ class CLIPB200:
         return out
 
 
-def resize_center_crop(image, n_px: int = 224):
-    """The PIL half of clip._transform: Resize(n_px, bicubic) on the shorter side (torchvision
-    rounding: longer side truncated), CenterCrop(n_px), convert("RGB").  Returns a PIL image;
-    everything after this point (ToTensor, Normalize) is exact per-pixel arithmetic, which the
-    uint8 entry points run on the GPU -- so PIL pixels in == reference transform out."""
-    from PIL import Image
-    w, h = image.size
-    if (w, h) != (n_px, n_px):
-        if w <= h:
-            nw, nh = n_px, int(n_px * h / w)
-        else:
-            nw, nh = int(n_px * w / h), n_px
-        image = image.resize((nw, nh), Image.BICUBIC)
-        left, top = int(round((nw - n_px) / 2.0)), int(round((nh - n_px) / 2.0))
-        image = image.crop((left, top, left + n_px, top + n_px))
-    return image.convert("RGB")
+from .pil_transform import image_to_u8, resize_center_crop  # noqa: E402,F401  (torch-free home: decode workers import it)
 
 
 def resize_center_crop_device(image_u8: torch.Tensor) -> torch.Tensor:
@@ -191,11 +176,6 @@ def resize_center_crop_device(image_u8: torch.Tensor) -> torch.Tensor:
         N.check(N.lib().cb_resize224_u8_device(C.c_void_p(src.data_ptr()), src.shape[0], src.shape[1],
                                                C.c_void_p(out.data_ptr()), stream))
     return out
-
-
-def image_to_u8(image, n_px: int = 224) -> np.ndarray:
-    """PIL image -> uint8 [n_px, n_px, 3] ready for encode_image's uint8 path."""
-    return np.array(resize_center_crop(image, n_px), dtype=np.uint8)
 
 
 def _transform(n_px: int = 224):

@@ -35,7 +35,7 @@ def list_images(base_path: str) -> List[str]:
 def _decode(tfn: str) -> Optional[np.ndarray]:
     """PIL decode + the reference's Resize/CenterCrop/RGB on the CPU -> uint8 [224,224,3]."""
     from PIL import Image
-    from .clip import image_to_u8
+    from .pil_transform import image_to_u8
     try:
         with Image.open(tfn) as im:
             return image_to_u8(im)
@@ -50,7 +50,7 @@ def _decode_full(tfn: str):
     resize; other modes (L, P, RGBA, ...) must be resized in their own mode before the RGB
     conversion (clip._transform order), so they take the CPU path and come back as [224,224,3]."""
     from PIL import Image
-    from .clip import image_to_u8
+    from .pil_transform import image_to_u8
     try:
         with Image.open(tfn) as im:
             if im.mode == "RGB":
@@ -68,6 +68,91 @@ def _read_bytes(tfn: str):
             return fh.read()
     except Exception:
         return None
+
+
+class _PilProcessPool:
+    """Pillow decode in worker PROCESSES (the thread pool tops out near 1.5 k images/s: about half of a
+    small file's decode time is Python code under the GIL).  Workers write uint8 pixels straight into
+    shared-memory blocks of [chunk,224,224,3]; only file names and ok-flags cross the pipes.  Each worker
+    is a plain `python -m clipb200.pil_transform` child (numpy + Pillow, no torch, no CUDA, nothing of
+    this process's __main__) driven by its own dispatcher thread over stdin/stdout."""
+
+    def __init__(self, nproc: int, chunk: int, depth: int = 3):
+        import subprocess
+        import threading
+        from multiprocessing import shared_memory
+        self.nproc, self.chunk, self.depth = nproc, chunk, depth
+        self.slots = [shared_memory.SharedMemory(create=True, size=chunk * 224 * 224 * 3) for _ in range(depth + 1)]
+        self.views = [np.ndarray((chunk, 224, 224, 3), dtype=np.uint8, buffer=s.buf) for s in self.slots]
+        self._local = threading.local()
+        self._children: List = []
+        self._lock = threading.Lock()
+        pkg_parent = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ)
+        env["PYTHONPATH"] = pkg_parent + os.pathsep + env.get("PYTHONPATH", "")
+
+        def child():
+            c = getattr(self._local, "child", None)
+            if c is None:
+                c = subprocess.Popen([sys.executable, "-m", "clipb200.pil_transform"], stdin=subprocess.PIPE,
+                                     stdout=subprocess.PIPE, env=env, text=True, bufsize=1)
+                self._local.child = c
+                with self._lock:
+                    self._children.append(c)
+            return c
+
+        self._child = child
+        self.pool = ThreadPoolExecutor(max_workers=nproc)
+
+    def _task(self, shm_name: str, row0: int, files: List[str]) -> List[bool]:
+        import json
+        c = self._child()
+        c.stdin.write(json.dumps({"shm": shm_name, "rows": self.chunk, "row0": row0, "files": files}) + "\n")
+        c.stdin.flush()
+        line = c.stdout.readline()
+        if not line:
+            raise RuntimeError("Pillow decode worker exited unexpectedly")
+        return json.loads(line)["ok"]
+
+    def chunks(self, todo: List[str]):
+        """Yield (names, pixels, ok) per chunk, in order; `pixels` is a view into a shared block that stays
+        valid until the generator is resumed."""
+        parts = [todo[i:i + self.chunk] for i in range(0, len(todo), self.chunk)]
+        pending = []
+
+        def submit(k: int, names: List[str]):
+            b = k % len(self.slots)
+            sub = max(1, -(-len(names) // (2 * self.nproc)))
+            futs = [self.pool.submit(self._task, self.slots[b].name, r0, names[r0:r0 + sub])
+                    for r0 in range(0, len(names), sub)]
+            return names, b, futs
+
+        k = 0
+        while k < len(parts) or pending:
+            while k < len(parts) and len(pending) < self.depth:
+                pending.append(submit(k, parts[k]))
+                k += 1
+            names, b, futs = pending.pop(0)
+            ok = np.array([flag for f in futs for flag in f.result()], dtype=bool)
+            yield names, self.views[b], ok
+
+    def close(self):
+        self.pool.shutdown(wait=True, cancel_futures=True)
+        for c in self._children:
+            try:
+                c.stdin.close()
+                c.wait(timeout=10)
+            except Exception:
+                c.kill()
+        self._children = []
+        self.views = []
+        for s in self.slots:
+            try:
+                s.close()
+                s.unlink()
+            except Exception:
+                pass
+        self.slots = []
 
 
 def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers: Optional[int] = None,
@@ -103,7 +188,13 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
                 print(".", end="", flush=True, file=out)
                 n_ok += 1
 
+    # decode workers: processes for folders worth their start-up (CLIPB200_PIL_PROCESSES=N pins the count,
+    # 0 keeps the thread pool), threads otherwise
+    env_np = os.environ.get("CLIPB200_PIL_PROCESSES")
+    nproc = int(env_np) if env_np is not None else (min(32, os.cpu_count() or 1) if (os.cpu_count() or 1) >= 4 else 0)
+    procs: Optional[_PilProcessPool] = None
     with ThreadPoolExecutor(max_workers=workers) as pool:
+      try:
         for base_path in folders:
             print(f"CLIPing {base_path}...", file=out)
             todo = []
@@ -117,6 +208,9 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
                     todo.append(tfn)
             inflight: List[Tuple[int, List[str], int]] = []   # (slot, names, n)
             slot, names, fill = 0, [], 0
+            use_procs = nproc > 0 and (env_np is not None or len(todo) >= 2048)
+            if use_procs and procs is None:
+                procs = _PilProcessPool(nproc, batch)
 
             def flush():
                 nonlocal slot, names, fill
@@ -134,22 +228,43 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
                 slot = (slot + 1) % nbuf
                 names, fill = [], 0
 
-            for tfn, px in zip(todo, pool.map(_decode, todo)):
-                if px is None:
-                    print("#", end="", flush=True, file=out)
-                    n_bad += 1
-                    continue
-                bufs[slot][fill] = torch.from_numpy(px)
-                names.append(tfn)
-                fill += 1
-                if fill == batch:
-                    flush()
+            if use_procs:
+                for names_, px, ok in procs.chunks(todo):
+                    good = np.nonzero(ok)[0]
+                    a = 0                               # bulk placement of the chunk's decoded rows
+                    while a < len(good):
+                        take = min(batch - fill, len(good) - a)
+                        sel = good[a:a + take]
+                        src = px[:take] if take == len(names_) else px[sel]
+                        bufs[slot][fill:fill + take] = torch.from_numpy(src)
+                        names.extend(names_[i] for i in sel)
+                        fill += take
+                        a += take
+                        if fill == batch:
+                            flush()
+                    for _ in range(len(names_) - len(good)):
+                        print("#", end="", flush=True, file=out)
+                        n_bad += 1
+            else:
+                for tfn, px in zip(todo, pool.map(_decode, todo)):
+                    if px is None:
+                        print("#", end="", flush=True, file=out)
+                        n_bad += 1
+                        continue
+                    bufs[slot][fill] = torch.from_numpy(px)
+                    names.append(tfn)
+                    fill += 1
+                    if fill == batch:
+                        flush()
             flush()
             N.check(L.cb_clip_sync(model.handle))
             for s_, nm_, n_ in inflight:
                 commit(nm_, outs[s_][:n_])
             inflight.clear()
             print(flush=True, file=out)
+      finally:
+        if procs is not None:
+            procs.close()
     return n_ok, n_bad
 
 

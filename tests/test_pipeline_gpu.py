@@ -226,3 +226,25 @@ def test_two_gpus_embed_one_folder(tmp_path, monkeypatch):
     b = np.stack([np.frombuffer(stores[1][k], dtype=np.float32) for k in sorted(stores[0])])
     # same decoder, same kernels, but a row's batch neighbours differ (tile shapes) -> fp16-level differences
     assert (a * b).sum(1).min() >= 0.99999
+
+
+def test_process_pool_decode_stores_the_same_bytes(tmp_path, monkeypatch):
+    """The Pillow path with decode worker processes (large folders) stores byte-identical vectors to the
+    in-process thread pool: same pixels in, same batches, same kernels."""
+    from clipb200 import clip, indexer, lmdb, weights
+    folder = str(tmp_path / "photos") + "/"
+    _make_folder(folder, n=200)
+    monkeypatch.chdir(tmp_path)
+    model = clip.CLIPB200(weights.synthetic_state_dict(0), device=0, max_image_batch=64, max_text_batch=1)
+    stores = []
+    for name, nproc in (("threads", "0"), ("procs", "3")):
+        monkeypatch.setenv("CLIPB200_PIL_PROCESSES", nproc)
+        env = lmdb.open(f"{name}.lmdb", map_size=1 << 30, max_dbs=4)
+        log = io.StringIO()
+        assert indexer.embed_folders([folder], env, model, batch=64, out=log) == (200, 1)
+        marks = log.getvalue().split("\n", 1)[1]
+        assert marks.count(".") == 200 and marks.count("#") == 1
+        with env.begin(db=env.open_db(b"fn_db")) as txn:
+            stores.append({bytes(k): bytes(v) for k, v in txn.cursor()})
+        env.close()
+    assert stores[0] == stores[1] and len(stores[0]) == 200
