@@ -316,6 +316,19 @@ def _nvjpeg_chunks(todo: List[str], chunk: int, decoder, dev, depth: int = 1):
             release(b)
 
 
+_decoders: dict = {}
+
+
+def _jpeg_decoder(device: int):
+    """One clipb200.jpeg.Decoder per device for the life of the process: creating one (an nvjpeg handle, two
+    back-end states, buffers and a stream per worker thread) costs ~0.3 s."""
+    from . import jpeg
+    key = (device, os.environ.get("CLIPB200_NVJPEG_THREADS", "0"))
+    if key not in _decoders:
+        _decoders[key] = jpeg.Decoder(device, int(key[1]))
+    return _decoders[key]
+
+
 def _device_pipeline(todo: List[str], model, batch: int, workers: int, decode: str, on_done, on_bad) -> None:
     """Embed `todo` on model.device: decode (nvjpeg through the C ABI, or Pillow in a thread pool) and
     resize on the GPU, batches of `batch` through the two-lane submit API.  Calls on_done(names, vecs)
@@ -330,10 +343,7 @@ def _device_pipeline(todo: List[str], model, batch: int, workers: int, decode: s
     with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=workers) as pool:
         dbuf = [torch.empty((batch, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
         dout = [torch.empty((batch, 512), dtype=torch.float32, device=dev) for _ in range(nbuf)]
-        decoder = None
-        if use_nvjpeg:
-            from . import jpeg
-            decoder = jpeg.Decoder(dev.index, int(os.environ.get("CLIPB200_NVJPEG_THREADS", "0")))
+        decoder = _jpeg_decoder(dev.index) if use_nvjpeg else None
 
         def to_device_224(item, dst):
             """item: a decoded uint8 array [h,w,3].  Writes [224,224,3] into dst."""
