@@ -210,7 +210,15 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
             slot, names, fill = 0, [], 0
             use_procs = nproc > 0 and (env_np is not None or len(todo) >= 2048)
             if use_procs and procs is None:
-                procs = _PilProcessPool(nproc, batch)
+                try:
+                    # the shared batch blocks live in /dev/shm: a worker writing past a too-small tmpfs dies of SIGBUS
+                    fs = os.statvfs("/dev/shm")
+                    if fs.f_bavail * fs.f_frsize < 6 * batch * 224 * 224 * 3:
+                        raise OSError("/dev/shm is too small for the shared batch blocks")
+                    procs = _PilProcessPool(nproc, batch)
+                except Exception as e:
+                    print(f"clipb200: decode worker processes unavailable ({e}); using the thread pool", file=sys.stderr)
+                    nproc, use_procs = 0, False
 
             def flush():
                 nonlocal slot, names, fill
