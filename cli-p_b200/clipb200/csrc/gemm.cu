@@ -103,7 +103,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // warp-uniform by construction
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -135,15 +135,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int KB = g.K / BK;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                int mt_, nt_;
-                decode(tile, mt_, nt_);
-                const int m_blk = mt_ * NCTA + (int)cta_rank, n_blk = nt_;
-                for (int kb = 0; kb < KB; kb++) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t *sa = smem + stage * C::STAGE_BYTES;
+        // warp-uniform producer loop; one elected lane arms the barrier and issues the TMA loads
+        uint32_t stage = 0, phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            int mt_, nt_;
+            decode(tile, mt_, nt_);
+            const int m_blk = mt_ * NCTA + (int)cta_rank, n_blk = nt_;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t *sa = smem + stage * C::STAGE_BYTES;
+                if (elect_one()) {
                     if (NCTA == 1) {
                         mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                         tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, &full[stage]);
@@ -160,12 +161,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tma_load_2d_2sm(sa + C::A_BYTES, &tmB, kb * BK, n_blk * BN + (int)cta_rank * C::B_ROWS,
                                         &full[stage]);
                     }
-                    if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
+            // the whole warp walks the schedule (uniform control flow, uniform registers); one elected lane
+            // issues the MMAs and commits
             constexpr uint32_t idesc = make_idesc(BM * NCTA, BN);
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -178,15 +182,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
                     const uint64_t da = make_smem_desc(sa);
                     const uint64_t db = make_smem_desc(sa + C::A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++) {
-                        // advance 16 elements = 32 B along K inside the swizzle atom: +2 in 16-B units
-                        umma_f16<NCTA>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; k++) {
+                            // advance 16 elements = 32 B along K inside the swizzle atom: +2 in 16-B units
+                            umma_f16<NCTA>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit<NCTA>(&empty[stage]);    // frees the smem slot (in both CTAs) when the MMAs retire
                     }
-                    umma_commit<NCTA>(&empty[stage]);    // frees the smem slot (in both CTAs) when the MMAs retire
+                    __syncwarp();
                     if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit<NCTA>(&tfull[as]);           // accumulator complete -> epilogue (both CTAs)
+                if (elect_one()) umma_commit<NCTA>(&tfull[as]);   // accumulator complete -> epilogue (both CTAs)
+                __syncwarp();
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }

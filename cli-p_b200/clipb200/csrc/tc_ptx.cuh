@@ -86,6 +86,21 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
         "}\n" ::"r"(smem_u32(bar)), "r"(cta)
         : "memory");
 }
+// true in exactly one lane of a converged warp.  The single-thread roles (TMA issue, MMA issue) run as
+// warp-uniform loops with the issuing instructions behind this predicate: the compiler then keeps
+// descriptors, coordinates and barrier addresses in uniform registers instead of broadcasting five
+// vector registers (ELECT + R2UR.BROADCAST) in front of every UTCHMMA / UTMALDG
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
