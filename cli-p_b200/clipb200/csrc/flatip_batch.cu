@@ -58,7 +58,7 @@ flatip_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
     const uint32_t cta_rank = cluster_ctarank();
     const bool leader = cta_rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -85,26 +85,29 @@ flatip_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int64_t tiles = (r1 - r0 + RN - 1) / RN;
     const int64_t items = tiles * q_blocks;          // item = (row tile, query block); query block fastest
 
+    // the TMA-issue and MMA-issue roles are warp-uniform loops with the issuing instructions behind
+    // elect.sync (as in gemm.cu): descriptors and coordinates stay in uniform registers
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int64_t it = pair; it < items; it += num_pairs) {
-                const int qb = (int)(it % q_blocks);
-                const int64_t n0 = r0 + (it / q_blocks) * RN;
-                const int qrow = qb * 2 * QM + (int)cta_rank * QM;
-                for (int kb = 0; kb < KB; kb++) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t *s = smem + stage * STAGE_BYTES;
+        uint32_t stage = 0, phase = 0;
+        for (int64_t it = pair; it < items; it += num_pairs) {
+            const int qb = (int)(it % q_blocks);
+            const int64_t n0 = r0 + (it / q_blocks) * RN;
+            const int qrow = qb * 2 * QM + (int)cta_rank * QM;
+            for (int kb = 0; kb < KB; kb++) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t *s = smem + stage * STAGE_BYTES;
+                if (elect_one()) {
                     if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
                     tma_load_2d_2sm(s, &tmQ, kb * BK, qrow, &full[stage]);                    // hi half
                     tma_load_2d_2sm(s + A_BYTES, &tmQ, 512 + kb * BK, qrow, &full[stage]);    // lo half
                     tma_load_2d_2sm(s + 2 * A_BYTES, &tmX, kb * BK, (int)(n0 + cta_rank * (RN / 2)), &full[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
             constexpr uint32_t idesc = make_idesc(2 * QM, RN);
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
             for (int64_t it = pair; it < items; it += num_pairs) {
@@ -117,14 +120,18 @@ flatip_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t dh = make_smem_desc(s), dl = make_smem_desc(s + A_BYTES);
                     const uint64_t db = make_smem_desc(s + 2 * A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++) umma_f16<2>(d_tmem, dh + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; k++) umma_f16<2>(d_tmem, dh + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++) umma_f16<2>(d_tmem, dl + 2 * k, db + 2 * k, idesc, 1u);
-                    umma_commit<2>(&empty[stage]);
+                        for (int k = 0; k < BK / 16; k++) umma_f16<2>(d_tmem, dl + 2 * k, db + 2 * k, idesc, 1u);
+                        umma_commit<2>(&empty[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit<2>(&tfull[as]);
+                if (elect_one()) umma_commit<2>(&tfull[as]);
+                __syncwarp();
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }
