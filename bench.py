@@ -453,11 +453,11 @@ def run_embed(args, torch, dist, rank, world, local):
         res["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
                            "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
                            # dram__bytes_read + dram__bytes_write of one c_fc launch (12800x3072x768, the
-                           # largest GEMM of the step) in profiles/r01_gemm_v5_cfc_ncu_raw.csv: 24.4 + 30.7 MB,
+                           # largest GEMM of the step) in profiles/r01_gemm_v6_cfc_ncu_raw.csv: 24.4 + 26.9 MB,
                            # against 103 MB of operands + output - the rest is served / absorbed by the L2
-                           "traffic": 55.1e6 if B == 256 else None,
+                           "traffic": 51.4e6 if B == 256 else None,
                            "traffic_note": "per launch of gemm_tcgen05_kernel<256,GELU,2> on the c_fc shape "
-                                           "(ncu --set full, profiles/r01_gemm_v5_cfc_ncu_raw.csv)",
+                                           "(ncu --set full, profiles/r01_gemm_v6_cfc_ncu_raw.csv)",
                            "kernel": "gemm_tcgen05_kernel (all GEMM launches of the step)",
                            "kernel_ms": ms.value / cnt.value,
                            "gemm_share_of_step": ms.value / 1e3 / one_lane_secs,
