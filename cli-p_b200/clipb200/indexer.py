@@ -465,39 +465,38 @@ def _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode) 
                 if len(key) > 511 or st.get(key) is not None or ft.get(key) is not None:
                     continue
                 todo.append(tfn)
-        if len(models) == 1:
-            _device_pipeline(todo, models[0], batch, workers, decode, commit, bad)
-        else:
-            R = len(models)
-            per = -(-len(todo) // R) if todo else 0
-            events: "queue.Queue" = queue.Queue(maxsize=4 * R)
-            errors: List[BaseException] = []
+        # one pipeline thread per device (also for a single GPU: decode/placement/submit then overlap with
+        # this thread's LMDB commits, ~45 k puts/s of pure Python)
+        R = len(models)
+        per = -(-len(todo) // R) if todo else 0
+        events: "queue.Queue" = queue.Queue(maxsize=4 * R)
+        errors: List[BaseException] = []
 
-            def run(r):
-                try:
-                    _device_pipeline(todo[r * per:(r + 1) * per], models[r], batch, workers, decode,
-                                     lambda nm, v: events.put(("ok", nm, v)), lambda nm: events.put(("bad", nm, None)))
-                except BaseException as e:      # surfaced in the committing thread
-                    errors.append(e)
-                finally:
-                    events.put(("end", None, None))
+        def run(r):
+            try:
+                _device_pipeline(todo[r * per:(r + 1) * per], models[r], batch, workers, decode,
+                                 lambda nm, v: events.put(("ok", nm, v)), lambda nm: events.put(("bad", nm, None)))
+            except BaseException as e:      # surfaced in the committing thread
+                errors.append(e)
+            finally:
+                events.put(("end", None, None))
 
-            threads = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(R)]
-            for t in threads:
-                t.start()
-            live = R
-            while live:
-                kind, nm, v = events.get()
-                if kind == "ok":
-                    commit(nm, v)
-                elif kind == "bad":
-                    bad(nm)
-                else:
-                    live -= 1
-            for t in threads:
-                t.join()
-            if errors:
-                raise errors[0]
+        threads = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(R)]
+        for t in threads:
+            t.start()
+        live = R
+        while live:
+            kind, nm, v = events.get()
+            if kind == "ok":
+                commit(nm, v)
+            elif kind == "bad":
+                bad(nm)
+            else:
+                live -= 1
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
         print(flush=True, file=out)
     return n_ok, n_bad
 
