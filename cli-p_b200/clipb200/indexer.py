@@ -403,10 +403,9 @@ def _device_pipeline(todo: List[str], model, batch: int, workers: int, decode: s
                     if fill == batch:
                         flush()
                 for i in np.nonzero(status != 0)[0]:
-                    if status[i] in (-1, 4):            # not a JPEG / not supported by nvjpeg: CPU decode
-                        yield names_[i], _decode_full(names_[i])
-                    else:
-                        yield names_[i], None
+                    # not a JPEG, or nvjpeg would not take it (CMYK, arithmetic coding, a damaged stream Pillow
+                    # may still read): Pillow decides; only an unreadable file is given up on at once
+                    yield names_[i], (None if status[i] == 1 else _decode_full(names_[i]))
 
         stream_items = nvjpeg_items() if use_nvjpeg else zip(todo, pool.map(_decode_full, todo))
         for tfn, item in stream_items:
