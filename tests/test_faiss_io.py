@@ -143,3 +143,25 @@ def test_l2_metric_header_and_metric_arg(tmp_path, rows):
     ix = fio.parse(p)
     assert ix.metric == 4
     np.testing.assert_array_equal(ix.rows(0, 37), rows)
+
+
+def test_random_ivf_partitions_round_trip(tmp_path):
+    """Property: whatever the k-means partition (empty lists, one list, every row its own list, full or
+    sparse size table), the flattened rows come back in add order."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(0, 120), d=st.sampled_from([4, 16]), nlist=st.integers(1, 14), sparse=st.booleans(),
+           seed=st.integers(0, 2 ** 16))
+    def check(n, d, nlist, sparse, seed):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        assign = rng.integers(0, max(1, nlist // (1 + seed % 3)), size=n)      # leaves some lists empty
+        p = str(tmp_path / "h.index")
+        open(p, "wb").write(ivf_bytes(x, assign, nlist, 1 + seed % 100, sparse=sparse))
+        ix = fio.parse(p)
+        assert (ix.kind, ix.d, ix.ntotal, ix.nlist) == ("ivf", d, n, nlist)
+        got = np.concatenate(list(ix.iter_rows(step=17))) if n else np.zeros((0, d), np.float32)
+        np.testing.assert_array_equal(got, x)
+
+    check()
