@@ -34,6 +34,26 @@ SIGNATURES = {
     "cb_abi_version": (_int, []),
     "cb_device_count": (_int, [C.POINTER(_int)]),
     "cb_launch_count": (_i64, [_int]),
+    "cb_tuning_set": (_int, [C.c_char_p, _i64]),
+    "cb_tuning_get": (_int, [C.c_char_p, C.POINTER(_i64)]),
+    "cb_flatip_device": (_int, [_p]),
+    "cb_flatip_p2p_init": (_int, [_p, _int, _int, _i64, _p]),
+    "cb_flatip_p2p_connect": (_int, [_p, _p]),
+    "cb_flatip_search_p2p_device": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p]),
+    "cb_flatip_p2p_status": (_int, [_p, C.POINTER(_int)]),
+    "cb_sharded_create": (_int, [_int, _int, _int, C.POINTER(_int), C.POINTER(_p)]),
+    "cb_sharded_free": (None, [_p]),
+    "cb_sharded_ntotal": (_i64, [_p]),
+    "cb_sharded_num_shards": (_int, [_p]),
+    "cb_sharded_shard": (_p, [_p, _int]),
+    "cb_sharded_reserve": (_int, [_p, _i64]),
+    "cb_sharded_reset": (_int, [_p]),
+    "cb_sharded_add": (_int, [_p, _i64, _p]),
+    "cb_sharded_add_device": (_int, [_p, _int, _i64, _p, _int, _p]),
+    "cb_sharded_search": (_int, [_p, _i64, _p, _i64, _p, _p]),
+    "cb_sharded_search_device": (_int, [_p, _i64, _p, _i64, _p, _p, _p]),
+    "cb_sharded_get_rows": (_int, [_p, _i64, _i64, _p]),
+    "cb_clip_ln_fold_status": (_int, [_p, C.POINTER(_int), C.POINTER(C.c_double)]),
     "cb_flatip_create": (_int, [_int, _int, _int, C.POINTER(_p)]),
     "cb_flatip_free": (None, [_p]),
     "cb_flatip_ntotal": (_i64, [_p]),
@@ -114,6 +134,35 @@ def device_count() -> int:
     n = _int(0)
     rc = lib().cb_device_count(C.byref(n))
     return n.value if rc == CB_OK else 0
+
+
+def tuning_set(name: str, value: int) -> None:
+    """Set a process-wide tuning knob (include/clipb200.h: cb_tuning_set); -1 restores the default."""
+    check(lib().cb_tuning_set(name.encode(), int(value)))
+
+
+def tuning_get(name: str) -> int:
+    v = _i64(0)
+    check(lib().cb_tuning_get(name.encode(), C.byref(v)))
+    return int(v.value)
+
+
+class tuning:
+    """Context manager: `with _native.tuning(gemm_bn=192): ...` (restores the previous values)."""
+
+    def __init__(self, **knobs):
+        self.knobs, self.prev = knobs, {}
+
+    def __enter__(self):
+        for k, v in self.knobs.items():
+            self.prev[k] = tuning_get(k)
+            tuning_set(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.prev.items():
+            tuning_set(k, v)
+        return False
 
 
 def launch_count(reset: bool = False) -> int:

@@ -63,6 +63,12 @@ class CLIPB200:
             N.lib().cb_clip_free(self.handle)
             self.handle = None
 
+    def ln_fold_status(self):
+        """(folded, min cosine of the calibration batch, -2.0 if the ln_fold knob decided)."""
+        f, c = C.c_int(0), C.c_double(0)
+        N.check(N.lib().cb_clip_ln_fold_status(self.handle, C.byref(f), C.byref(c)))
+        return bool(f.value), float(c.value)
+
     def __del__(self):
         try:
             self.close()
@@ -193,17 +199,25 @@ def _transform(n_px: int = 224):
 def load(name: str = "ViT-B/32", device: Union[str, torch.device] = "cuda", jit: bool = False,
          download_root: str = None, max_image_batch: int = 256, max_text_batch: int = 64):
     """clip.load(...) -> (model, transform).  Weights come from $CLIP_WEIGHTS (an OpenAI
-    ViT-B-32.pt TorchScript archive or state_dict) or, when unset, from the seeded synthetic
-    initialisation -- no checkpoint can be downloaded offline."""
+    ViT-B-32.pt TorchScript archive or state_dict).  The reference downloads the checkpoint here;
+    offline that is impossible, and embedding a photo collection with random weights would fill
+    vectors.lmdb with rows that resume-by-key never recomputes -- so without a checkpoint this
+    raises.  CLIPB200_SYNTHETIC_WEIGHTS=1 (tests, benches) opts into the seeded synthetic model."""
     if name != "ViT-B/32":
         raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
     dev = torch.device(device)
     path = os.environ.get("CLIP_WEIGHTS")
     if path:
         sd = _weights.load_state_dict(path)
-    else:
-        print("clipb200: CLIP_WEIGHTS not set -- using seeded synthetic ViT-B/32 weights", file=sys.stderr)
+    elif os.environ.get("CLIPB200_SYNTHETIC_WEIGHTS", "0") == "1":
+        print("clipb200: CLIPB200_SYNTHETIC_WEIGHTS=1 -- seeded synthetic ViT-B/32 weights (embeddings are "
+              "meaningless for real images)", file=sys.stderr)
         sd = _weights.synthetic_state_dict(0)
+    else:
+        raise RuntimeError(
+            "clip.load: set CLIP_WEIGHTS to an OpenAI ViT-B-32.pt (TorchScript archive or state_dict); no "
+            "checkpoint can be downloaded offline.  CLIPB200_SYNTHETIC_WEIGHTS=1 opts into seeded synthetic "
+            "weights for tests and benches.")
     index = dev.index if (dev.type == "cuda" and dev.index is not None) else (
         torch.cuda.current_device() if dev.type == "cuda" else 0)
     model = CLIPB200(sd, device=index, max_image_batch=max_image_batch, max_text_batch=max_text_batch,

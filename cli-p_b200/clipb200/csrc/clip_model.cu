@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 #include "vit_kernels.cuh"
 
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -74,7 +75,8 @@ struct cb_clip {
     int max_img = 0, max_txt = 0;
     std::map<std::string, Param> params;
     std::map<std::string, std::vector<float>> host;   // fp32 copies needed to fold LayerNorm at finalize
-    bool ln_fold = true;          // CLIPB200_NO_LN_FOLD=1 keeps separate LayerNorm launches
+    bool ln_fold = true;          // ln_1 / ln_2 folded into the QKV / c_fc GEMMs (decided by cb_clip_finalize)
+    double ln_fold_cos = -2.0;    // calibration result: min cosine folded vs unfolded (-2: not calibrated)
     bool finalized = false;
     LayerW vis[LAYERS], txt[LAYERS];
     const __half *conv1_w = nullptr, *vproj_w = nullptr, *tproj_w = nullptr;
@@ -253,8 +255,12 @@ GemmArgs mk(const __half *A, const __half *W, const float *bias, const __half *r
 // 12 residual attention blocks over x [B*L, W] (in place)
 int run_blocks(cb_clip *m, Ws &w, const LayerW *lw, int W, int heads, int B, int L, bool causal, cudaStream_t s) {
     const int rows = B * L;
-    // perf experiments only (results become wrong): CLIPB200_SKIP=1 drops ln_1/ln_2, =2 drops attention
-    static const int skip = getenv("CLIPB200_SKIP") ? atoi(getenv("CLIPB200_SKIP")) : 0;
+#ifdef CLIPB200_EXPERIMENTS
+    // perf experiments only (results become wrong): skip=1 drops ln_1/ln_2, =2 drops attention
+    const int skip = tune(T_SKIP) > 0 ? (int)tune(T_SKIP) : 0;
+#else
+    constexpr int skip = 0;
+#endif
     if (m->ln_fold) {
         // ln_1 / ln_2 live inside the QKV / c_fc GEMMs: A operand = raw residual stream, per-row
         // statistics come from whoever wrote x last (ln_pre / text_embed for block 0, then the
@@ -353,6 +359,79 @@ int text_forward(cb_clip *m, Ws &w, int B, const int32_t *ids_dev, float *out_de
     return CB_OK;
 }
 
+constexpr double kFoldMinCos = 0.9998;   // folded vs unfolded embeddings on the calibration batch
+
+// restore the raw in_proj / c_fc weights and biases from the host copies (undo fold_layernorm)
+int unfold_layernorm(cb_clip *m, const char *prefix, int W) {
+    for (int i = 0; i < LAYERS; i++) {
+        const std::string b = std::string(prefix) + ".resblocks." + std::to_string(i) + ".";
+        for (const char *suffix : {"attn.in_proj_weight", "attn.in_proj_bias", "mlp.c_fc.weight", "mlp.c_fc.bias"}) {
+            auto it = m->host.find(b + suffix);
+            if (it == m->host.end()) { set_error("cb_clip_finalize: host copy of %s%s missing", b.c_str(), suffix); return CB_ERR_INVALID; }
+            const bool w = ends_with(it->first, "weight");
+            int rc = upload(m, it->first, it->second.data(), (int64_t)it->second.size(), w);
+            if (rc) return rc;
+        }
+    }
+    return CB_OK;
+}
+
+// A small deterministic forward pass through both towers with the CURRENT binding (folded or not):
+// four images (noise, ramp, checkerboard, flat grey + noise) and four token rows.  out = the
+// un-normalised embeddings, [rows][512].
+int calibration_pass(cb_clip *m, std::vector<float> &out) {
+    out.clear();
+    const bool was = m->finalized;
+    m->finalized = true;
+    int rc = CB_OK;
+    uint32_t lcg = 12345u;
+    auto rnd = [&]() { lcg = lcg * 1664525u + 1013904223u; return lcg >> 24; };
+    const int nb = std::min(4, m->max_img);
+    if (nb > 0) {
+        std::vector<uint8_t> img((size_t)nb * 224 * 224 * 3);
+        for (int b = 0; b < nb; b++)
+            for (int y = 0; y < 224; y++)
+                for (int x = 0; x < 224; x++)
+                    for (int c = 0; c < 3; c++) {
+                        uint32_t v;
+                        switch (b) {
+                            case 0: v = rnd(); break;
+                            case 1: v = (uint32_t)((x + y * 2 + c * 40) * 255 / (224 * 3 + 80)); break;
+                            case 2: v = (((x >> 4) ^ (y >> 4)) & 1) ? 230u - 20u * c : 25u + 30u * c; break;
+                            default: v = 118u + (rnd() & 15u); break;
+                        }
+                        img[(((size_t)b * 224 + y) * 224 + x) * 3 + c] = (uint8_t)std::min(v, 255u);
+                    }
+        CB_CUDA(cudaMemcpyAsync(m->d_img, img.data(), img.size(), cudaMemcpyHostToDevice, m->stream));
+        rc = encode_u8_chunk(m, m->ws, nb, m->d_img, m->d_out, 0, m->stream);
+        if (rc == CB_OK) {
+            out.resize((size_t)nb * ED);
+            CB_CUDA(cudaMemcpyAsync(out.data(), m->d_out, out.size() * 4, cudaMemcpyDeviceToHost, m->stream));
+            CB_CUDA(cudaStreamSynchronize(m->stream));
+        }
+    }
+    const int nt = std::min(4, m->max_txt);
+    if (rc == CB_OK && nt > 0) {
+        std::vector<int32_t> ids((size_t)nt * TL, 0);
+        for (int b = 0; b < nt; b++) {
+            const int len = 3 + b * 5;
+            ids[(size_t)b * TL] = 49406;
+            for (int t = 1; t <= len; t++) ids[(size_t)b * TL + t] = 1000 + (int)((rnd() * 151u + (uint32_t)t * 977u) % 39000u);
+            ids[(size_t)b * TL + len + 1] = 49407;
+        }
+        CB_CUDA(cudaMemcpyAsync(m->d_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, m->stream));
+        rc = text_forward(m, m->ws, nt, m->d_ids, m->d_out, 0, m->stream);
+        if (rc == CB_OK) {
+            const size_t at = out.size();
+            out.resize(at + (size_t)nt * ED);
+            CB_CUDA(cudaMemcpyAsync(out.data() + at, m->d_out, (size_t)nt * ED * 4, cudaMemcpyDeviceToHost, m->stream));
+            CB_CUDA(cudaStreamSynchronize(m->stream));
+        }
+    }
+    m->finalized = was;
+    return rc;
+}
+
 constexpr int kGraphMaxBatch = 32;
 
 void drop_graphs(cb_clip *m) {
@@ -371,7 +450,7 @@ void drop_graphs(cb_clip *m) {
 template <typename Body>
 int graphed_forward(cb_clip *m, int kind, int b, int normalize, const void *in_dev, void *slot_in, size_t in_bytes,
                     float *out_dev, cudaStream_t s, Body &&body) {
-    static const bool off = getenv("CLIPB200_NO_GRAPH") && atoi(getenv("CLIPB200_NO_GRAPH"));
+    const bool off = tune(T_NO_GRAPH) > 0;
     if (off || m->timing || b > kGraphMaxBatch) return body(in_dev, out_dev, s);
     cb_clip::GraphEntry &e = m->graphs[(kind << 16) | (b << 1) | (normalize ? 1 : 0)];
     if (!e.seen || e.failed) {
@@ -524,20 +603,60 @@ int cb_clip_finalize(cb_clip *m) {
     rc |= need(m, "ln_final.bias", TW, false, &m->lnf_b);
     rc |= need(m, "text_projection", 1ll * TW * ED, true, &m->tproj_w);
     if (rc) return CB_ERR_INVALID;
-    m->ln_fold = !(getenv("CLIPB200_NO_LN_FOLD") && atoi(getenv("CLIPB200_NO_LN_FOLD")));
-    if (m->ln_fold) {
+    // class token row before ln_pre = class_embedding + positional_embedding[0]
+    {
+        std::vector<float> a(VW), b(VW);
+        CB_CUDA(cudaMemcpy(a.data(), cls_emb, VW * 4, cudaMemcpyDeviceToHost));
+        CB_CUDA(cudaMemcpy(b.data(), m->vpos, VW * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < VW; i++) a[i] += b[i];
+        CB_CUDA(cudaMemcpy(m->cls_pos, a.data(), VW * 4, cudaMemcpyHostToDevice));
+    }
+    // LayerNorm fold (ln_fold knob: 0 never, 1 always, unset = fold if a calibration batch agrees with the
+    // unfolded model).  The folded GEMM consumes the raw fp16 residual stream and removes mean * colsum
+    // afterwards, with variance = E[x^2] - mean^2 in fp32: exact enough for sane activations, but a
+    // checkpoint whose residual stream carries a large common-mode offset would lose digits there.  The
+    // reference normalises in fp32 BEFORE the fp16 cast, so when the two disagree the unfolded form wins.
+    const int64_t knob = tune(T_LN_FOLD);
+    m->ln_fold_cos = -2.0;
+    std::vector<float> e_plain;
+    if (knob != 1) {
+        m->ln_fold = false;
+        if ((rc = bind_blocks(m, "visual.transformer", VW, m->vis))) return rc;
+        if ((rc = bind_blocks(m, "transformer", TW, m->txt))) return rc;
+        if (knob < 0 && (rc = calibration_pass(m, e_plain))) return rc;
+    }
+    if (knob != 0) {
         if ((rc = fold_layernorm(m, "visual.transformer", VW))) return rc;
         if ((rc = fold_layernorm(m, "transformer", TW))) return rc;
+        m->ln_fold = true;
+        if ((rc = bind_blocks(m, "visual.transformer", VW, m->vis))) return rc;
+        if ((rc = bind_blocks(m, "transformer", TW, m->txt))) return rc;
+        if (knob < 0) {
+            std::vector<float> e_fold;
+            if ((rc = calibration_pass(m, e_fold))) return rc;
+            double worst = 1.0;
+            for (size_t r = 0; r + ED <= e_fold.size() && r + ED <= e_plain.size(); r += ED) {
+                double ab = 0, aa = 0, bb = 0;
+                for (int i = 0; i < ED; i++) {
+                    ab += (double)e_fold[r + i] * e_plain[r + i];
+                    aa += (double)e_fold[r + i] * e_fold[r + i];
+                    bb += (double)e_plain[r + i] * e_plain[r + i];
+                }
+                const double c = (aa > 0 && bb > 0) ? ab / std::sqrt(aa * bb) : -1.0;
+                worst = std::min(worst, std::isfinite(c) ? c : -1.0);
+            }
+            m->ln_fold_cos = worst;
+            if (worst < kFoldMinCos) {
+                // put the raw weights / biases back and run LayerNorm as its own launch
+                if ((rc = unfold_layernorm(m, "visual.transformer", VW))) return rc;
+                if ((rc = unfold_layernorm(m, "transformer", TW))) return rc;
+                m->ln_fold = false;
+                if ((rc = bind_blocks(m, "visual.transformer", VW, m->vis))) return rc;
+                if ((rc = bind_blocks(m, "transformer", TW, m->txt))) return rc;
+            }
+        }
     }
     m->host.clear();
-    if ((rc = bind_blocks(m, "visual.transformer", VW, m->vis))) return rc;
-    if ((rc = bind_blocks(m, "transformer", TW, m->txt))) return rc;
-    // class token row before ln_pre = class_embedding + positional_embedding[0]
-    std::vector<float> a(VW), b(VW);
-    CB_CUDA(cudaMemcpy(a.data(), cls_emb, VW * 4, cudaMemcpyDeviceToHost));
-    CB_CUDA(cudaMemcpy(b.data(), m->vpos, VW * 4, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < VW; i++) a[i] += b[i];
-    CB_CUDA(cudaMemcpy(m->cls_pos, a.data(), VW * 4, cudaMemcpyHostToDevice));
     m->finalized = true;
     return CB_OK;
 }
@@ -739,6 +858,13 @@ int cb_clip_encode_text(cb_clip *m, int64_t B, const int32_t *ids_host, float *o
         CB_CUDA(cudaMemcpyAsync(out_host + lo * ED, m->d_out, (size_t)b * ED * 4, cudaMemcpyDeviceToHost, m->stream));
         CB_CUDA(cudaStreamSynchronize(m->stream));
     }
+    return CB_OK;
+}
+
+int cb_clip_ln_fold_status(cb_clip *m, int *folded, double *min_cosine) {
+    CB_REQUIRE(m && folded && min_cosine, "cb_clip_ln_fold_status: null argument");
+    *folded = m->ln_fold ? 1 : 0;
+    *min_cosine = m->ln_fold_cos;
     return CB_OK;
 }
 

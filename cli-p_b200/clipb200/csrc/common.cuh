@@ -13,6 +13,26 @@ namespace cb {
 void set_error(const char *fmt, ...);
 extern thread_local int64_t g_launches;
 
+// Process-wide tuning knobs (cb_tuning_set / cb_tuning_get, clipb200.h).  Each is read from its
+// CLIPB200_* environment variable ONCE, when the library is loaded; -1 = unset (built-in default).
+// Launch paths read a relaxed atomic, never the environment.
+enum Tune : int {
+    T_GEMM_BN = 0,        // CLIPB200_GEMM_BN            force the GEMM N tile (64 / 128 / 192 / 256)
+    T_GEMM_NCTA,          // CLIPB200_GEMM_NCTA          force the GEMM cluster size (1 / 2)
+    T_GEMM_STAGES,        // CLIPB200_GEMM_STAGES        cap the TMA ring depth
+    T_GEMM_RASTER,        // CLIPB200_GEMM_RASTER        tile rasterisation (0 n-fastest, 1 m-fastest, g>=2 grouped)
+    T_BATCH_MIN_NQ,       // CLIPB200_BATCH_MIN_NQ       smallest query batch served by the tensor-core search
+    T_NO_GRAPH,           // CLIPB200_NO_GRAPH           1: never replay small forward passes as CUDA graphs
+    T_LN_BLOCKS_PER_SM,   // CLIPB200_LN_BLOCKS_PER_SM   LayerNorm grid size
+    T_LN_FOLD,            // CLIPB200_LN_FOLD            0: keep ln_1 / ln_2 as separate launches; 1: force the fold;
+                          //                             unset: fold, checked by the calibration pass of cb_clip_finalize
+    T_GEMM_DEBUG,         // CLIPB200_GEMM_DEBUG         (only in -DCLIPB200_EXPERIMENTS builds) result-corrupting probes
+    T_SKIP,               // CLIPB200_SKIP               (only in -DCLIPB200_EXPERIMENTS builds)
+    T_SEARCH_LINBINS,     // CLIPB200_SEARCH_LINBINS     0: first-level radix on float bits instead of linear score bins
+    T_COUNT
+};
+int64_t tune(Tune t);
+
 #define CB_CUDA(expr)                                                              \
     do {                                                                           \
         cudaError_t _e = (expr);                                                   \

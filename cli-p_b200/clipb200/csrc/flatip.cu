@@ -19,11 +19,13 @@
 // round trip, any k from 1 to ntotal.  Order is the total order (-score, id): results
 // do not depend on the launch geometry, so 1-GPU and sharded results are identical.
 #include "common.cuh"
+#include "flatip.cuh"
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace cb {
 
@@ -32,10 +34,10 @@ struct BatchWs;
 BatchWs *batch_ws_new();
 void batch_ws_delete(BatchWs *w);
 int flatip_search_batch(BatchWs *w, const void *rows_f16, int64_t n, int device, int64_t nq, const float *q_dev,
-                        int64_t k, float *D_dev, int64_t *I_dev, int64_t id_base, cudaStream_t s,
-                        bool *overflowed);
+                        int64_t k, float *D_dev, int64_t *I_dev, const IdMap &ids, const PeerOut &po,
+                        const float *max_norm2, cudaStream_t s);
+int batch_ws_stats(BatchWs *w, int64_t *rescued, cudaStream_t s);
 
-constexpr int kD = 512;
 constexpr int kBins0 = 2048;           // 11 + 11 + 10 bit digits
 constexpr int kMaxNQ = 4;              // queries sharing one pass over the shard (register budget)
 constexpr int kSortSmem = 4096;        // composite keys sorted in shared memory
@@ -125,28 +127,6 @@ __device__ __forceinline__ float reduce_rows(float (&v)[R], int lane) {
     float t = v[0];
     for (; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
     return t;
-}
-
-__device__ __forceinline__ float dot8_h(const uint4 &u, const float *q) {
-    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-    float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
-    float2 c = __half22float2(h[2]), d = __half22float2(h[3]);
-    float s = a.x * q[0];
-    s = fmaf(a.y, q[1], s);
-    s = fmaf(b.x, q[2], s);
-    s = fmaf(b.y, q[3], s);
-    s = fmaf(c.x, q[4], s);
-    s = fmaf(c.y, q[5], s);
-    s = fmaf(d.x, q[6], s);
-    s = fmaf(d.y, q[7], s);
-    return s;
-}
-__device__ __forceinline__ float dot4_f(const uint4 &u, const float *q) {
-    float s = __uint_as_float(u.x) * q[0];
-    s = fmaf(__uint_as_float(u.y), q[1], s);
-    s = fmaf(__uint_as_float(u.z), q[2], s);
-    s = fmaf(__uint_as_float(u.w), q[3], s);
-    return s;
 }
 
 // K1: one pass over the shard.  Row = 512 elements: fp16 -> 64 x 16 B chunks (lane
@@ -284,18 +264,14 @@ __device__ void bitonic_desc(uint64_t *a, uint32_t n_pow2) {
     }
 }
 
-__device__ __forceinline__ uint64_t make_comp(uint32_t key, uint32_t id) {
-    return ((uint64_t)key << 32) | (uint64_t)(0xffffffffu - id);
-}
-
 // write one query's sorted winners + faiss padding
-__device__ void emit_sorted(const uint64_t *a, uint32_t count, int64_t k, int64_t id_base,
+__device__ void emit_sorted(const uint64_t *a, uint32_t count, int64_t k, const IdMap &ids,
                             float *D, int64_t *I) {
     for (int64_t j = threadIdx.x; j < k; j += blockDim.x) {
         if (j < count) {
             uint64_t c = a[j];
             D[j] = key2f((uint32_t)(c >> 32));
-            I[j] = id_base + (int64_t)(0xffffffffu - (uint32_t)c);
+            I[j] = map_id(ids, 0xffffffffu - (uint32_t)c);
         } else {
             D[j] = -3.4028234663852886e38f;
             I[j] = -1;
@@ -303,10 +279,12 @@ __device__ void emit_sorted(const uint64_t *a, uint32_t count, int64_t k, int64_
     }
 }
 
-// K3: gather winners; the last block orders exact ties by id, sorts and writes D/I.
+// K3: gather winners; the last block orders exact ties by id, sorts and writes D/I (possibly
+// straight into the root GPU's mailbox, see PeerOut), then clears the query's workspace so the
+// next search needs no memset.
 __global__ void __launch_bounds__(kPostThreads)
 flatip_collect_kernel(const float *__restrict__ scores_all, int64_t n, int64_t stride, QueryWs *ws,
-                      uint64_t *cand_all, uint32_t cand_cap, int64_t k, int64_t id_base,
+                      uint64_t *cand_all, uint32_t cand_cap, int64_t k, const IdMap ids, const PeerOut po,
                       float *D_all, int64_t *I_all) {
     QueryWs *w = ws + blockIdx.y;
     const SelState st = w->st;
@@ -375,28 +353,49 @@ flatip_collect_kernel(const float *__restrict__ scores_all, int64_t n, int64_t s
         for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) s_sort[i] = i < count ? __ldcg(cand + i) : 0ull;
         __syncthreads();
         bitonic_desc(s_sort, p2);
-        emit_sorted(s_sort, count, k, id_base, D, I);
+        peer_wait_slot(po);
+        emit_sorted(s_sort, count, k, ids, D, I);
     } else {
         for (uint32_t i = count + threadIdx.x; i < p2; i += blockDim.x) cand[i] = 0ull;
         __syncthreads();
         bitonic_desc(cand, p2);   // global-memory sort for very large k (REPL paging)
-        emit_sorted(cand, count, k, id_base, D, I);
+        peer_wait_slot(po);
+        emit_sorted(cand, count, k, ids, D, I);
     }
+    peer_signal(po, 1u);
+    // every other block of this query has retired: reset histograms + selection state for the next search
+    uint32_t *wz = reinterpret_cast<uint32_t *>(w);
+    for (uint32_t i = threadIdx.x; i < sizeof(QueryWs) / 4; i += blockDim.x) wz[i] = 0u;
 }
 
-__global__ void fill_empty_kernel(float *D, int64_t *I, int64_t total) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
+// empty shard: every slot is padding.  One block, so it can take part in the peer protocol.
+__global__ void fill_empty_kernel(float *D, int64_t *I, int64_t total, const PeerOut po, uint32_t nq) {
+    peer_wait_slot(po);
+    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
         D[i] = -3.4028234663852886e38f;
         I[i] = -1;
     }
+    peer_signal(po, nq);
 }
+
+// what the root's merge waits for / announces (null pointers: plain merge of resident lists)
+struct MergeSync {
+    const uint32_t *done = nullptr;   // [R] cumulative queries delivered per rank
+    uint32_t need_done = 0;           // every rank has delivered this search once done[r] >= need_done
+    uint32_t *consumed = nullptr;     // += 1 per merged query (frees the slot for the search after next)
+    uint32_t *error = nullptr;
+};
 
 // merge R sorted per-shard lists: one block per query
 __global__ void __launch_bounds__(kPostThreads)
-topk_merge_kernel(int R, int64_t nq, int64_t k, const float *__restrict__ D_in,
-                  const int64_t *__restrict__ I_in, int64_t shard_stride_D, int64_t shard_stride_I,
-                  float *D_out, int64_t *I_out, float *g_s, int64_t *g_i, uint32_t p2) {
+topk_merge_kernel(int R, int64_t nq, int64_t k, const float *D_in,
+                  const int64_t *I_in, int64_t shard_stride_D, int64_t shard_stride_I,
+                  float *D_out, int64_t *I_out, float *g_s, int64_t *g_i, uint32_t p2, const MergeSync ms) {
+    if (ms.done) {
+        // the lists arrive over NVLink: acquire every rank's delivery counter before reading them
+        if (threadIdx.x < (unsigned)R) spin_until(ms.done + threadIdx.x, ms.need_done, ms.error);
+        __syncthreads();
+    }
     // scores/ids are sorted as (key, ~id) pairs; ids are global (up to 2^63), so keep
     // them beside the key instead of packing them
     extern __shared__ unsigned char s_raw[];
@@ -410,8 +409,8 @@ topk_merge_kernel(int R, int64_t nq, int64_t k, const float *__restrict__ D_in,
         if (i < tot) {
             uint32_t r = i / (uint32_t)k, j = i % (uint32_t)k;
             size_t src = (size_t)q * k + j;
-            ss[i] = D_in[(size_t)r * shard_stride_D + src];
-            si[i] = I_in[(size_t)r * shard_stride_I + src];
+            ss[i] = __ldcg(D_in + (size_t)r * shard_stride_D + src);    // L2: peers wrote these lines
+            si[i] = __ldcg(I_in + (size_t)r * shard_stride_I + src);
         } else { ss[i] = 0.f; si[i] = -1; }
     }
     __syncthreads();
@@ -441,6 +440,42 @@ topk_merge_kernel(int R, int64_t nq, int64_t k, const float *__restrict__ D_in,
         D_out[q * k + j] = valid ? ss[j] : -3.4028234663852886e38f;
         I_out[q * k + j] = valid ? si[j] : -1;
     }
+    if (ms.consumed) {
+        // this query's slot lines have been read (they sit in ss / si): let the peers reuse them
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            red_release_sys_add(ms.consumed, 1u);
+        }
+    }
+}
+
+// max over rows of ||x||^2 (as stored), kept per shard: bounds |<q - fp16(q), x>| in the batch path
+template <bool F16>
+__global__ void rownorm_max_kernel(const uint4 *__restrict__ rows, int64_t n, float *max_norm2) {
+    constexpr int ROW_V4 = F16 ? 64 : 128;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float best = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
+        float s = 0.f;
+        for (int c = lane; c < ROW_V4; c += 32) {
+            const uint4 u = ld_stream_v4(rows + r * ROW_V4 + c);
+            if (F16) {
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; e++) { float2 f = __half22float2(h[e]); s = fmaf(f.x, f.x, s); s = fmaf(f.y, f.y, s); }
+            } else {
+                const float f[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
+#pragma unroll
+                for (int e = 0; e < 4; e++) s = fmaf(f[e], f[e], s);
+            }
+        }
+        s = warp_sum(s);
+        best = fmaxf(best, s);
+    }
+    // norms are >= 0: the float bit pattern orders like an unsigned integer
+    if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<unsigned int *>(max_norm2), __float_as_uint(best));
 }
 
 __global__ void f32_to_f16_kernel(const float4 *__restrict__ src, uint2 *__restrict__ dst, int64_t n4) {
@@ -467,6 +502,38 @@ __global__ void f16_to_f32_kernel(const __half *__restrict__ src, float *__restr
 // =====================================================================================
 using namespace cb;
 
+namespace {
+
+// Root mailbox (device memory of rank 0, mapped into every rank): a 256-byte header followed by
+// kSlots x world result slots of `cap` elements each (D block fp32, then I block int64).
+constexpr int kSlots = 2;                 // a rank may run one search ahead of the root's merge
+constexpr size_t kMailHeader = 256;
+constexpr size_t kOffDone = 0;            // uint32 done[kMaxRanks]
+constexpr size_t kOffConsumed = 64;       // uint32 consumed
+constexpr size_t kOffError = 68;          // uint32 error
+
+struct P2P {
+    bool attached = false;
+    int rank = 0, world = 1;
+    int64_t cap = 0;                      // elements per (slot, rank)
+    char *own = nullptr;                  // allocation owned by this index (rank 0 only)
+    char *root = nullptr;                 // the root's mailbox as addressable from this device
+    bool root_is_ipc = false;             // opened with cudaIpcOpenMemHandle (close on free)
+    uint32_t seq = 0;                     // searches issued so far
+    uint32_t total = 0;                   // queries issued so far (cumulative, wraps)
+    uint32_t ring[kSlots] = {0};          // `total` after the search that last used each slot
+    // root only: merge scratch for very large k
+    size_t slot_bytes() const { return (size_t)cap * 12; }
+    float *slot_D(int slot, int r) const { return reinterpret_cast<float *>(root + kMailHeader + ((size_t)slot * world + r) * slot_bytes()); }
+    int64_t *slot_I(int slot, int r) const { return reinterpret_cast<int64_t *>(reinterpret_cast<char *>(slot_D(slot, r)) + (size_t)cap * 4); }
+    uint32_t *done() const { return reinterpret_cast<uint32_t *>(root + kOffDone); }
+    uint32_t *consumed() const { return reinterpret_cast<uint32_t *>(root + kOffConsumed); }
+    uint32_t *error() const { return reinterpret_cast<uint32_t *>(root + kOffError); }
+    size_t bytes() const { return kMailHeader + (size_t)kSlots * world * slot_bytes(); }
+};
+
+}  // namespace
+
 struct cb_index {
     int d = kD;
     int dtype = CB_F16;
@@ -475,12 +542,18 @@ struct cb_index {
     int64_t capacity = 0;
     void *rows = nullptr;            // [capacity][512] of dtype
     cudaStream_t stream = nullptr;   // used by the host-pointer entry points
+    cudaEvent_t add_ev = nullptr;    // orders ix->stream after add_device() calls on foreign streams
+    float *max_norm2 = nullptr;      // device scalar: max ||row||^2 over the shard (as stored)
     // search workspace
     float *scores = nullptr;         // [kMaxNQ][score_stride]
     int64_t score_stride = 0;
-    QueryWs *ws = nullptr;           // [kMaxNQ]
+    QueryWs *ws = nullptr;           // [kMaxNQ]; zero between searches (the collect kernel re-zeroes it)
+    bool ws_dirty = true;
     uint64_t *cand = nullptr;        // [kMaxNQ][cand_cap]
     uint32_t cand_cap = 0;
+    // global-id segments of a shard inside a multi-shard index (cb_sharded): device copies
+    int64_t *seg_dev = nullptr;      // [2][seg_cap]: local starts, then global starts
+    int seg_cap = 0, nseg = 0;
     // pinned + device staging for the host-pointer entry points
     float *h_q = nullptr, *d_q = nullptr;
     int64_t q_cap = 0;               // queries
@@ -488,11 +561,12 @@ struct cb_index {
     int64_t *h_I = nullptr, *d_I = nullptr;
     int64_t out_cap = 0;             // nq*k elements
     void *d_stage = nullptr;         // add() staging
-    void *h_stage = nullptr;
     int64_t stage_bytes = 0;
     int scan_blocks_per_sm[2][3] = {{0}};
+    int sms = 0;
     cb::BatchWs *bws = nullptr;      // workspace of the tensor-core batch path
-    int64_t n_batch_searches = 0, n_batch_overflows = 0;
+    int64_t n_batch_searches = 0;
+    P2P p2p;
     // optional live timing of the scan kernel (bench.py roofline): event pairs on the
     // launching stream, resolved lazily by cb_flatip_timing_read
     bool timing = false;
@@ -501,6 +575,12 @@ struct cb_index {
     int ev_n = 0;
 
     size_t row_bytes() const { return (size_t)d * (dtype == CB_F16 ? 2 : 4); }
+    IdMap idmap(int64_t id_base) const {
+        IdMap m;
+        if (nseg > 0) { m.seg_local = seg_dev; m.seg_global = seg_dev + seg_cap; m.nseg = nseg; }
+        m.id_base = id_base;
+        return m;
+    }
 };
 
 static int grow_rows(cb_index *ix, int64_t need, cudaStream_t s) {
@@ -509,6 +589,8 @@ static int grow_rows(cb_index *ix, int64_t need, cudaStream_t s) {
     cap = (cap + 63) / 64 * 64;
     void *p = nullptr;
     CB_CUDA(cudaMalloc(&p, (size_t)cap * ix->row_bytes()));
+    // the old buffer may still be read by searches queued on the index's own stream
+    if (ix->stream && ix->stream != s) CB_CUDA(cudaStreamSynchronize(ix->stream));
     if (ix->rows && ix->ntotal)
         CB_CUDA(cudaMemcpyAsync(p, ix->rows, (size_t)ix->ntotal * ix->row_bytes(),
                                 cudaMemcpyDeviceToDevice, s));
@@ -528,7 +610,10 @@ static int ensure_ws(cb_index *ix, int64_t k_eff) {
         CB_CUDA(cudaMalloc(&ix->scores, (size_t)kMaxNQ * s * sizeof(float)));
         ix->score_stride = s;
     }
-    if (!ix->ws) CB_CUDA(cudaMalloc(&ix->ws, sizeof(QueryWs) * kMaxNQ));
+    if (!ix->ws) {
+        CB_CUDA(cudaMalloc(&ix->ws, sizeof(QueryWs) * kMaxNQ));
+        ix->ws_dirty = true;
+    }
     uint32_t p2 = 256;
     while ((int64_t)p2 < k_eff) p2 <<= 1;
     if (p2 > ix->cand_cap) {
@@ -551,12 +636,10 @@ static int launch_scan(cb_index *ix, const float *q_dev, int nq_valid, uint32_t 
         CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kScanThreads, smem));
         if (bps < 1) bps = 1;
     }
-    int sms = kNumSMs;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
     constexpr int R = F16 ? 8 : 4;
     int64_t groups = (ix->ntotal + R - 1) / R;
     int64_t want = (groups + (kScanThreads / 32) - 1) / (kScanThreads / 32);
-    int grid = (int)std::min<int64_t>((int64_t)sms * bps, std::max<int64_t>(want, 1));
+    int grid = (int)std::min<int64_t>((int64_t)ix->sms * bps, std::max<int64_t>(want, 1));
     const bool timed = ix->timing && ix->ev_n < cb_index::kEv;
     if (timed) {
         if (!ix->ev0[ix->ev_n]) {
@@ -575,12 +658,15 @@ static int launch_scan(cb_index *ix, const float *q_dev, int nq_valid, uint32_t 
     return CB_OK;
 }
 
+// one pass of the streaming path over <= kMaxNQ queries: scan, 2 x refine, collect
 static int search_tile(cb_index *ix, int nq, const float *q_dev, int64_t k, float *D_dev,
-                       int64_t *I_dev, int64_t id_base, cudaStream_t s) {
+                       int64_t *I_dev, const IdMap &ids, const PeerOut &po, cudaStream_t s) {
     const int64_t n = ix->ntotal;
     const int64_t k_eff = std::min<int64_t>(k, n);
-    // reset histograms + state (k_rem is seeded by the scan kernel's last block)
-    CB_CUDA(cudaMemsetAsync(ix->ws, 0, sizeof(QueryWs) * nq, s));
+    // histograms + state are zero between searches: the collect kernel's last block re-zeroes them
+    // (k_rem is seeded by the scan kernel's last block).  Only a search that failed half way needs a memset.
+    if (ix->ws_dirty) CB_CUDA(cudaMemsetAsync(ix->ws, 0, sizeof(QueryWs) * kMaxNQ, s));
+    ix->ws_dirty = true;
     const bool f16 = ix->dtype == CB_F16;
     int rc;
     if (nq == 1) rc = f16 ? launch_scan<1, true>(ix, q_dev, nq, (uint32_t)k_eff, s) : launch_scan<1, false>(ix, q_dev, nq, (uint32_t)k_eff, s);
@@ -588,18 +674,169 @@ static int search_tile(cb_index *ix, int nq, const float *q_dev, int64_t k, floa
     else rc = f16 ? launch_scan<4, true>(ix, q_dev, nq, (uint32_t)k_eff, s) : launch_scan<4, false>(ix, q_dev, nq, (uint32_t)k_eff, s);
     if (rc) return rc;
 
-    int sms = kNumSMs;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
     const int64_t n4 = (n + 3) / 4;
-    int gx = (int)std::min<int64_t>((int64_t)sms * 4, std::max<int64_t>((n4 + kPostThreads - 1) / kPostThreads, 1));
+    int gx = (int)std::min<int64_t>((int64_t)ix->sms * 4, std::max<int64_t>((n4 + kPostThreads - 1) / kPostThreads, 1));
     dim3 grid(gx, nq);
     for (int pass = 1; pass <= 2; pass++) {
         flatip_refine_kernel<<<grid, kPostThreads, 0, s>>>(ix->scores, n, ix->score_stride, ix->ws, pass);
         CB_LAUNCH_CHECK();
     }
     flatip_collect_kernel<<<grid, kPostThreads, 0, s>>>(ix->scores, n, ix->score_stride, ix->ws, ix->cand,
-                                                        ix->cand_cap, k, id_base, D_dev, I_dev);
+                                                        ix->cand_cap, k, ids, po, D_dev, I_dev);
     CB_LAUNCH_CHECK();
+    ix->ws_dirty = false;
+    return CB_OK;
+}
+
+// Dispatch of one search over this shard.  nq < batch_min (or fp32 storage, or k > 1024, or a tiny
+// shard) streams the shard once per 4 queries (HBM-bound scan); larger batches on fp16 shards run the
+// tcgen05 GEMM with a fused per-query threshold filter and exact fp32 re-scoring (tensor-bound).
+// Nothing here synchronises.  With `po` set, every query's list is delivered to the root's mailbox.
+static int search_core(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev, int64_t *I_dev,
+                       const IdMap &ids, const PeerOut &po, cudaStream_t s) {
+    if (ix->ntotal == 0) {
+        fill_empty_kernel<<<1, 256, 0, s>>>(D_dev, I_dev, nq * k, po, (uint32_t)nq);
+        CB_LAUNCH_CHECK();
+        return CB_OK;
+    }
+    // The GEMM pass over 10M rows costs about the same whatever nq <= 128 is, the streaming scan 1.5 ms for
+    // one query, 1.9 ms for two, 2.9 ms for four and another pass per four after that.  Small shards keep a
+    // higher threshold: there both paths are bounded by their launch counts, not by the pass over the rows.
+    int64_t batch_min = ix->ntotal >= (1ll << 20) ? 3 : 16;
+    if (tune(T_BATCH_MIN_NQ) > 0) batch_min = tune(T_BATCH_MIN_NQ);
+    if (nq >= batch_min && ix->dtype == CB_F16 && k <= 1024 && ix->ntotal >= 8192) {
+        if (!ix->bws) ix->bws = batch_ws_new();
+        int brc = flatip_search_batch(ix->bws, ix->rows, ix->ntotal, ix->device, nq, q_dev, k, D_dev, I_dev, ids, po,
+                                      ix->max_norm2, s);
+        if (brc) return brc;
+        ix->n_batch_searches++;
+        return CB_OK;
+    }
+    int rc = ensure_ws(ix, std::min<int64_t>(k, ix->ntotal));
+    if (rc) return rc;
+    for (int64_t q0 = 0; q0 < nq; q0 += kMaxNQ) {
+        int t = (int)std::min<int64_t>(kMaxNQ, nq - q0);
+        rc = search_tile(ix, t, q_dev + q0 * ix->d, k, D_dev + q0 * k, I_dev + q0 * k, ids, po, s);
+        if (rc) return rc;
+    }
+    return CB_OK;
+}
+
+static int launch_merge(int R, int64_t nq, int64_t k, const float *D_in, const int64_t *I_in, int64_t shard_stride_D,
+                        int64_t shard_stride_I, float *D_out, int64_t *I_out, const MergeSync &ms, cudaStream_t s) {
+    uint32_t p2 = 2;
+    while ((int64_t)p2 < (int64_t)R * k) p2 <<= 1;
+    size_t smem = (size_t)p2 * 12;
+    float *g_s = nullptr;
+    int64_t *g_i = nullptr;
+    if (smem > 96 * 1024) {
+        // very large k: sort in global scratch (allocated per call; rare REPL paging case)
+        CB_CUDA(cudaMallocAsync(&g_i, (size_t)nq * p2 * 8, s));
+        CB_CUDA(cudaMallocAsync(&g_s, (size_t)nq * p2 * 4, s));
+        smem = 0;
+    } else if (smem > 48 * 1024) {
+        CB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    }
+    topk_merge_kernel<<<(unsigned)nq, kPostThreads, smem, s>>>(R, nq, k, D_in, I_in, shard_stride_D, shard_stride_I,
+                                                               D_out, I_out, g_s, g_i, p2, ms);
+    CB_LAUNCH_CHECK();
+    if (g_s) { CB_CUDA(cudaFreeAsync(g_s, s)); CB_CUDA(cudaFreeAsync(g_i, s)); }
+    return CB_OK;
+}
+
+static int ensure_q(cb_index *ix, int64_t nq) {
+    if (nq <= ix->q_cap) return CB_OK;
+    cudaFreeHost(ix->h_q); cudaFree(ix->d_q);
+    ix->h_q = nullptr; ix->d_q = nullptr; ix->q_cap = 0;
+    CB_CUDA(cudaMallocHost(&ix->h_q, (size_t)nq * ix->d * 4));
+    CB_CUDA(cudaMalloc(&ix->d_q, (size_t)nq * ix->d * 4));
+    ix->q_cap = nq;
+    return CB_OK;
+}
+
+static int ensure_out(cb_index *ix, int64_t elems) {
+    if (elems <= ix->out_cap) return CB_OK;
+    cudaFreeHost(ix->h_D); cudaFreeHost(ix->h_I); cudaFree(ix->d_D); cudaFree(ix->d_I);
+    ix->h_D = nullptr; ix->h_I = nullptr; ix->d_D = nullptr; ix->d_I = nullptr; ix->out_cap = 0;
+    CB_CUDA(cudaMallocHost(&ix->h_D, (size_t)elems * 4));
+    CB_CUDA(cudaMallocHost(&ix->h_I, (size_t)elems * 8));
+    CB_CUDA(cudaMalloc(&ix->d_D, (size_t)elems * 4));
+    CB_CUDA(cudaMalloc(&ix->d_I, (size_t)elems * 8));
+    ix->out_cap = elems;
+    return CB_OK;
+}
+
+// ---- peer delivery: attach / one search ---------------------------------------------------
+static void p2p_detach(cb_index *ix) {
+    P2P &p = ix->p2p;
+    if (p.root_is_ipc && p.root) cudaIpcCloseMemHandle(p.root);
+    if (p.own) cudaFree(p.own);
+    p = P2P();
+}
+
+static int p2p_alloc_root(cb_index *ix, int world, int64_t max_elems) {
+    P2P &p = ix->p2p;
+    p.rank = 0;
+    p.world = world;
+    p.cap = (std::max<int64_t>(max_elems, 1024) + 1) / 2 * 2;
+    CB_CUDA(cudaMalloc(&p.own, p.bytes()));
+    CB_CUDA(cudaMemset(p.own, 0, kMailHeader));
+    p.root = p.own;
+    p.attached = true;
+    return CB_OK;
+}
+
+// The local part of a sharded search: this rank's top-k goes into the root's mailbox slot.
+// Returns the slot and the cumulative query count after this search.
+static int p2p_local_search(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, int64_t id_base, cudaStream_t s,
+                            int *slot_out, uint32_t *total_out) {
+    P2P &p = ix->p2p;
+    const int slot = (int)(p.seq % kSlots);
+    PeerOut po;
+    po.done = p.done() + p.rank;
+    po.consumed = p.consumed();
+    po.need_consumed = p.ring[slot];          // the search that last used this slot must be merged
+    po.error = p.error();
+    int rc = search_core(ix, nq, q_dev, k, p.slot_D(slot, p.rank), p.slot_I(slot, p.rank), ix->idmap(id_base), po, s);
+    if (rc) return rc;
+    p.total += (uint32_t)nq;
+    p.ring[slot] = p.total;
+    p.seq++;
+    *slot_out = slot;
+    *total_out = p.total;
+    return CB_OK;
+}
+
+static int p2p_root_merge(cb_index *ix, int slot, uint32_t total, int64_t nq, int64_t k, float *D_dev, int64_t *I_dev,
+                          cudaStream_t s) {
+    P2P &p = ix->p2p;
+    MergeSync ms;
+    ms.done = p.done();
+    ms.need_done = total;
+    ms.consumed = p.consumed();
+    ms.error = p.error();
+    const int64_t stride_D = (int64_t)(p.slot_bytes() / 4), stride_I = (int64_t)(p.slot_bytes() / 8);
+    return launch_merge(p.world, nq, k, p.slot_D(slot, 0), p.slot_I(slot, 0), stride_D, stride_I, D_dev, I_dev, ms, s);
+}
+
+static int set_segments(cb_index *ix, const std::vector<int64_t> &local, const std::vector<int64_t> &global) {
+    const int n = (int)local.size();
+    if (n <= 1) {            // a single run of ids is just an offset
+        ix->nseg = 0;
+        return CB_OK;
+    }
+    DeviceGuard g(ix->device);
+    if (n > ix->seg_cap) {
+        if (ix->seg_dev) CB_CUDA(cudaFree(ix->seg_dev));
+        ix->seg_dev = nullptr;
+        const int cap = std::max(64, n * 2);
+        CB_CUDA(cudaMalloc(&ix->seg_dev, (size_t)cap * 2 * sizeof(int64_t)));
+        ix->seg_cap = cap;
+    }
+    CB_CUDA(cudaStreamSynchronize(ix->stream));
+    CB_CUDA(cudaMemcpy(ix->seg_dev, local.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(ix->seg_dev + ix->seg_cap, global.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    ix->nseg = n;
     return CB_OK;
 }
 
@@ -624,10 +861,15 @@ int cb_flatip_create(int d, int storage_dtype, int device, cb_index **out) {
     ix->d = d;
     ix->dtype = storage_dtype;
     ix->device = device;
+    ix->sms = kNumSMs;
+    cudaDeviceGetAttribute(&ix->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->add_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->max_norm2, 256);
+    if (e == cudaSuccess) e = cudaMemset(ix->max_norm2, 0, 256);
     if (e != cudaSuccess) {
-        set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
-        delete ix;
+        set_error("cb_flatip_create: %s", cudaGetErrorString(e));
+        cb_flatip_free(ix);
         return CB_ERR_CUDA;
     }
     *out = ix;
@@ -638,14 +880,17 @@ void cb_flatip_free(cb_index *ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
+    p2p_detach(ix);
     cudaFree(ix->rows); cudaFree(ix->scores); cudaFree(ix->ws); cudaFree(ix->cand);
     cudaFree(ix->d_q); cudaFree(ix->d_D); cudaFree(ix->d_I); cudaFree(ix->d_stage);
-    cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_D); cudaFreeHost(ix->h_I); cudaFreeHost(ix->h_stage);
+    cudaFree(ix->max_norm2); cudaFree(ix->seg_dev);
+    cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_D); cudaFreeHost(ix->h_I);
     cb::batch_ws_delete(ix->bws);
     for (int i = 0; i < cb_index::kEv; i++) {
         if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
         if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]);
     }
+    if (ix->add_ev) cudaEventDestroy(ix->add_ev);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -653,6 +898,7 @@ void cb_flatip_free(cb_index *ix) {
 int64_t cb_flatip_ntotal(const cb_index *ix) { return ix ? ix->ntotal : -1; }
 int cb_flatip_dim(const cb_index *ix) { return ix ? ix->d : -1; }
 int cb_flatip_storage_dtype(const cb_index *ix) { return ix ? ix->dtype : -1; }
+int cb_flatip_device(const cb_index *ix) { return ix ? ix->device : -1; }
 const void *cb_flatip_device_rows(const cb_index *ix) { return ix ? ix->rows : nullptr; }
 
 int cb_flatip_reserve(cb_index *ix, int64_t n_rows) {
@@ -664,7 +910,11 @@ int cb_flatip_reserve(cb_index *ix, int64_t n_rows) {
 
 int cb_flatip_reset(cb_index *ix) {
     CB_REQUIRE(ix != nullptr, "cb_flatip_reset: null index");
+    DeviceGuard g(ix->device);
+    CB_CUDA(cudaStreamSynchronize(ix->stream));
+    CB_CUDA(cudaMemset(ix->max_norm2, 0, 4));
     ix->ntotal = 0;
+    ix->nseg = 0;
     return CB_OK;
 }
 
@@ -692,6 +942,18 @@ int cb_flatip_add_device(cb_index *ix, int64_t n, const void *x_dev, int src_dty
         int grid = (int)std::min<int64_t>(kNumSMs * 8, (elems + 255) / 256);
         f16_to_f32_kernel<<<grid, 256, 0, s>>>((const __half *)x_dev, (float *)dst, elems);
         CB_LAUNCH_CHECK();
+    }
+    {
+        const int grid = (int)std::min<int64_t>((int64_t)ix->sms * 8, (n + 7) / 8);
+        if (ix->dtype == CB_F16) rownorm_max_kernel<true><<<grid, 256, 0, s>>>((const uint4 *)dst, n, ix->max_norm2);
+        else rownorm_max_kernel<false><<<grid, 256, 0, s>>>((const uint4 *)dst, n, ix->max_norm2);
+        CB_LAUNCH_CHECK();
+    }
+    // the host-pointer entry points (search, get_rows) run on the index's own stream: order it after
+    // this add, whatever stream the caller used
+    if (s != ix->stream) {
+        CB_CUDA(cudaEventRecord(ix->add_ev, s));
+        CB_CUDA(cudaStreamWaitEvent(ix->stream, ix->add_ev, 0));
     }
     ix->ntotal += n;
     return CB_OK;
@@ -731,38 +993,7 @@ int cb_flatip_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_
     if (nq == 0) return CB_OK;
     CB_REQUIRE(q_dev && D_dev && I_dev, "cb_flatip_search_device: null buffer");
     DeviceGuard g(ix->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (ix->ntotal == 0) {
-        int64_t tot = nq * k;
-        fill_empty_kernel<<<(int)std::min<int64_t>(1024, (tot + 255) / 256), 256, 0, s>>>(D_dev, I_dev, tot);
-        CB_LAUNCH_CHECK();
-        return CB_OK;
-    }
-    // query batches: tensor-core GEMM + fused threshold filter (fp16 shards, k <= 1024).
-    // The GEMM pass costs ~3.3 ms over 10M rows whatever nq <= 256 is (one 256-query tile column); the
-    // streaming scan costs 1.5 ms for one query, 2.9 ms for four and another pass per four after that,
-    // so the crossover is at five queries (profiles/r01_batch_crossover.txt).  Small shards keep the old
-    // threshold: there both paths are bounded by their launch counts, not by the pass over the rows.
-    int64_t batch_min = ix->ntotal >= (1ll << 20) ? 5 : 16;
-    if (const char *e = getenv("CLIPB200_BATCH_MIN_NQ")) batch_min = atoll(e);
-    if (nq >= batch_min && ix->dtype == CB_F16 && k <= 1024 && ix->ntotal >= 8192) {
-        if (!ix->bws) ix->bws = batch_ws_new();
-        bool overflowed = false;
-        int brc = flatip_search_batch(ix->bws, ix->rows, ix->ntotal, ix->device, nq, q_dev, k, D_dev, I_dev,
-                                      id_base, s, &overflowed);
-        if (brc) return brc;
-        ix->n_batch_searches++;
-        if (!overflowed) return CB_OK;
-        ix->n_batch_overflows++;      // adversarial row order: redo exactly with the scan path
-    }
-    int rc = ensure_ws(ix, std::min<int64_t>(k, ix->ntotal));
-    if (rc) return rc;
-    for (int64_t q0 = 0; q0 < nq; q0 += kMaxNQ) {
-        int t = (int)std::min<int64_t>(kMaxNQ, nq - q0);
-        rc = search_tile(ix, t, q_dev + q0 * ix->d, k, D_dev + q0 * k, I_dev + q0 * k, id_base, s);
-        if (rc) return rc;
-    }
-    return CB_OK;
+    return search_core(ix, nq, q_dev, k, D_dev, I_dev, ix->idmap(id_base), PeerOut(), (cudaStream_t)stream);
 }
 
 int cb_flatip_search(cb_index *ix, int64_t nq, const float *q_host, int64_t k, float *D_host,
@@ -773,25 +1004,12 @@ int cb_flatip_search(cb_index *ix, int64_t nq, const float *q_host, int64_t k, f
     if (nq == 0) return CB_OK;
     CB_REQUIRE(q_host && D_host && I_host, "cb_flatip_search: null buffer");
     DeviceGuard g(ix->device);
-    if (nq > ix->q_cap) {
-        cudaFreeHost(ix->h_q); cudaFree(ix->d_q);
-        ix->h_q = nullptr; ix->d_q = nullptr;
-        CB_CUDA(cudaMallocHost(&ix->h_q, (size_t)nq * ix->d * 4));
-        CB_CUDA(cudaMalloc(&ix->d_q, (size_t)nq * ix->d * 4));
-        ix->q_cap = nq;
-    }
-    if (nq * k > ix->out_cap) {
-        cudaFreeHost(ix->h_D); cudaFreeHost(ix->h_I); cudaFree(ix->d_D); cudaFree(ix->d_I);
-        ix->h_D = nullptr; ix->h_I = nullptr; ix->d_D = nullptr; ix->d_I = nullptr;
-        CB_CUDA(cudaMallocHost(&ix->h_D, (size_t)nq * k * 4));
-        CB_CUDA(cudaMallocHost(&ix->h_I, (size_t)nq * k * 8));
-        CB_CUDA(cudaMalloc(&ix->d_D, (size_t)nq * k * 4));
-        CB_CUDA(cudaMalloc(&ix->d_I, (size_t)nq * k * 8));
-        ix->out_cap = nq * k;
-    }
+    int rc;
+    if ((rc = ensure_q(ix, nq))) return rc;
+    if ((rc = ensure_out(ix, nq * k))) return rc;
     memcpy(ix->h_q, q_host, (size_t)nq * ix->d * 4);
     CB_CUDA(cudaMemcpyAsync(ix->d_q, ix->h_q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, ix->stream));
-    int rc = cb_flatip_search_device(ix, nq, ix->d_q, k, ix->d_D, ix->d_I, 0, ix->stream);
+    rc = cb_flatip_search_device(ix, nq, ix->d_q, k, ix->d_D, ix->d_I, 0, ix->stream);
     if (rc) return rc;
     CB_CUDA(cudaMemcpyAsync(ix->h_D, ix->d_D, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
     CB_CUDA(cudaMemcpyAsync(ix->h_I, ix->d_I, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ix->stream));
@@ -810,31 +1028,100 @@ int cb_topk_merge_device(int R, int64_t nq, int64_t k, const float *D_in, const 
     CB_REQUIRE((int64_t)R * k < (1ll << 30), "cb_topk_merge_device: R*k too large");
     if (shard_stride_D <= 0) shard_stride_D = nq * k;
     if (shard_stride_I <= 0) shard_stride_I = nq * k;
-    cudaStream_t s = (cudaStream_t)stream;
-    uint32_t p2 = 2;
-    while ((int64_t)p2 < (int64_t)R * k) p2 <<= 1;
-    size_t smem = (size_t)p2 * 12;
-    float *g_s = nullptr;
-    int64_t *g_i = nullptr;
-    if (smem > 96 * 1024) {
-        // very large k: sort in global scratch (allocated per call; rare REPL paging case)
-        CB_CUDA(cudaMallocAsync(&g_i, (size_t)nq * p2 * 8, s));
-        CB_CUDA(cudaMallocAsync(&g_s, (size_t)nq * p2 * 4, s));
-        smem = 0;
-    } else if (smem > 48 * 1024) {
-        CB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    return launch_merge(R, nq, k, D_in, I_in, shard_stride_D, shard_stride_I, D_out, I_out, MergeSync(),
+                        (cudaStream_t)stream);
+}
+
+// ---- sharded search, one process per GPU: NVLink peer delivery instead of a collective --------
+int cb_flatip_p2p_init(cb_index *ix, int rank, int world, int64_t max_elems, void *ipc_handle_out64) {
+    CB_REQUIRE(ix && ipc_handle_out64, "cb_flatip_p2p_init: null argument");
+    CB_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
+               "cb_flatip_p2p_init: rank %d / world %d out of range (at most %d ranks)", rank, world, kMaxRanks);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(ix->device);
+    CB_CUDA(cudaStreamSynchronize(ix->stream));
+    p2p_detach(ix);
+    memset(ipc_handle_out64, 0, 64);
+    if (rank == 0) {
+        int rc = p2p_alloc_root(ix, world, max_elems);
+        if (rc) return rc;
+        if (world > 1) {
+            cudaIpcMemHandle_t h;
+            CB_CUDA(cudaIpcGetMemHandle(&h, ix->p2p.own));
+            memcpy(ipc_handle_out64, &h, 64);
+        }
+    } else {
+        ix->p2p.rank = rank;
+        ix->p2p.world = world;
+        ix->p2p.cap = (std::max<int64_t>(max_elems, 1024) + 1) / 2 * 2;
     }
-    topk_merge_kernel<<<(unsigned)nq, kPostThreads, smem, s>>>(R, nq, k, D_in, I_in, shard_stride_D, shard_stride_I,
-                                                               D_out, I_out, g_s, g_i, p2);
-    CB_LAUNCH_CHECK();
-    if (g_s) { CB_CUDA(cudaFreeAsync(g_s, s)); CB_CUDA(cudaFreeAsync(g_i, s)); }
     return CB_OK;
 }
 
-int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_overflow_fallbacks) {
-    CB_REQUIRE(ix && n_batch_searches && n_overflow_fallbacks, "cb_flatip_batch_stats: null argument");
+int cb_flatip_p2p_connect(cb_index *ix, const void *root_ipc_handle64) {
+    CB_REQUIRE(ix != nullptr, "cb_flatip_p2p_connect: null index");
+    P2P &p = ix->p2p;
+    if (p.rank == 0) {
+        CB_REQUIRE(p.attached, "cb_flatip_p2p_connect: call cb_flatip_p2p_init first");
+        return CB_OK;
+    }
+    CB_REQUIRE(root_ipc_handle64 != nullptr, "cb_flatip_p2p_connect: null handle");
+    CB_REQUIRE(p.cap > 0, "cb_flatip_p2p_connect: call cb_flatip_p2p_init first");
+    DeviceGuard g(ix->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, root_ipc_handle64, 64);
+    void *ptr = nullptr;
+    CB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p.root = (char *)ptr;
+    p.root_is_ipc = true;
+    p.attached = true;
+    return CB_OK;
+}
+
+int cb_flatip_search_p2p_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
+                                int64_t *I_dev, int64_t id_base, void *stream) {
+    CB_REQUIRE(ix != nullptr, "cb_flatip_search_p2p_device: null index");
+    P2P &p = ix->p2p;
+    CB_REQUIRE(p.attached, "cb_flatip_search_p2p_device: not attached (cb_flatip_p2p_init / _connect)");
+    CB_REQUIRE(nq >= 0, "cb_flatip_search_p2p_device: nq < 0");
+    CB_REQUIRE(k > 0 && k <= p.cap, "cb_flatip_search_p2p_device: k = %lld does not fit a mailbox slot of %lld elements",
+               (long long)k, (long long)p.cap);
+    if (nq == 0) return CB_OK;
+    CB_REQUIRE(q_dev != nullptr, "cb_flatip_search_p2p_device: null query");
+    CB_REQUIRE(p.rank != 0 || (D_dev && I_dev), "cb_flatip_search_p2p_device: the root needs output buffers");
+    DeviceGuard g(ix->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t chunk = std::max<int64_t>(1, p.cap / k);       // queries per mailbox slot
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t m = std::min(chunk, nq - q0);
+        int slot = 0;
+        uint32_t total = 0;
+        int rc = p2p_local_search(ix, m, q_dev + q0 * ix->d, k, id_base, s, &slot, &total);
+        if (rc) return rc;
+        if (p.rank == 0 && (rc = p2p_root_merge(ix, slot, total, m, k, D_dev + q0 * k, I_dev + q0 * k, s))) return rc;
+    }
+    return CB_OK;
+}
+
+int cb_flatip_p2p_status(cb_index *ix, int *error) {
+    CB_REQUIRE(ix && error, "cb_flatip_p2p_status: null argument");
+    *error = 0;
+    if (!ix->p2p.attached) return CB_OK;
+    DeviceGuard g(ix->device);
+    uint32_t e = 0;
+    CB_CUDA(cudaMemcpy(&e, ix->p2p.error(), 4, cudaMemcpyDeviceToHost));
+    *error = (int)e;
+    return CB_OK;
+}
+
+int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_rescued) {
+    CB_REQUIRE(ix && n_batch_searches && n_rescued, "cb_flatip_batch_stats: null argument");
     *n_batch_searches = ix->n_batch_searches;
-    *n_overflow_fallbacks = ix->n_batch_overflows;
+    *n_rescued = 0;
+    if (ix->bws) {
+        DeviceGuard g(ix->device);
+        return batch_ws_stats(ix->bws, n_rescued, ix->stream);
+    }
     return CB_OK;
 }
 
@@ -888,6 +1175,305 @@ int cb_flatip_get_rows(cb_index *ix, int64_t start, int64_t n, float *out_host) 
         CB_CUDA(cudaMemcpyAsync(out_host + lo * ix->d, ix->d_stage, (size_t)elems * 4, cudaMemcpyDeviceToHost, ix->stream));
         CB_CUDA(cudaStreamSynchronize(ix->stream));
     }
+    return CB_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================
+// cb_sharded: one index over several GPUs driven by ONE process (the REPL of query-index.py)
+// =====================================================================================
+struct cb_sharded {
+    int d = kD, dtype = CB_F16;
+    std::vector<cb_index *> sh;
+    std::vector<int> devices;
+    // per shard: runs of consecutive global ids (local start, global start, count)
+    struct Seg { int64_t local, global, count; };
+    std::vector<std::vector<Seg>> segs;
+    int64_t ntotal = 0;
+    std::vector<cudaEvent_t> ev_done;     // shard r's local search has been queued / finished
+    cudaEvent_t ev_q = nullptr;           // the query is ready on the root stream
+    int64_t mail_cap = 0;
+};
+
+namespace {
+
+int sharded_sync_segments(cb_sharded *S, int r) {
+    std::vector<int64_t> l, g;
+    for (const auto &sg : S->segs[r]) { l.push_back(sg.local); g.push_back(sg.global); }
+    return set_segments(S->sh[r], l, g);
+}
+
+void sharded_note_rows(cb_sharded *S, int r, int64_t local0, int64_t global0, int64_t count) {
+    auto &v = S->segs[r];
+    if (!v.empty() && v.back().local + v.back().count == local0 && v.back().global + v.back().count == global0)
+        v.back().count += count;          // still one run
+    else
+        v.push_back({local0, global0, count});
+}
+
+int64_t shard_id_base(const cb_sharded *S, int r) {
+    const auto &v = S->segs[r];
+    return v.size() == 1 ? v[0].global - v[0].local : 0;
+}
+
+// (re)allocate the root mailbox so that nq x k elements fit one slot
+int sharded_ensure_mailbox(cb_sharded *S, int64_t elems) {
+    const int R = (int)S->sh.size();
+    if (elems <= S->mail_cap && S->sh[0]->p2p.attached) return CB_OK;
+    const int64_t cap = std::max<int64_t>(elems, 128 * 1024);
+    for (cb_index *ix : S->sh) {
+        DeviceGuard g(ix->device);
+        CB_CUDA(cudaStreamSynchronize(ix->stream));
+        p2p_detach(ix);
+    }
+    {
+        DeviceGuard g(S->sh[0]->device);
+        int rc = p2p_alloc_root(S->sh[0], R, cap);
+        if (rc) return rc;
+    }
+    for (int r = 1; r < R; r++) {
+        P2P &p = S->sh[r]->p2p;
+        p.rank = r;
+        p.world = R;
+        p.cap = S->sh[0]->p2p.cap;
+        p.root = S->sh[0]->p2p.root;      // same process: peer access makes the pointer valid on every device
+        p.attached = true;
+    }
+    S->mail_cap = S->sh[0]->p2p.cap;
+    return CB_OK;
+}
+
+// q: device pointer on devices[0] (q_host == nullptr) or pinned host memory; outputs on devices[0];
+// s0: stream of devices[0] that the outputs are ordered on
+int sharded_search_impl(cb_sharded *S, int64_t nq, const float *q_dev0, const float *q_host, int64_t k,
+                        float *D_dev0, int64_t *I_dev0, cudaStream_t s0) {
+    const int R = (int)S->sh.size();
+    cb_index *root = S->sh[0];
+    if (R == 1) {
+        DeviceGuard g(root->device);
+        const float *q = q_dev0;
+        if (q_host) {
+            CB_CUDA(cudaMemcpyAsync(root->d_q, q_host, (size_t)nq * kD * 4, cudaMemcpyHostToDevice, s0));
+            q = root->d_q;
+        }
+        return search_core(root, nq, q, k, D_dev0, I_dev0, root->idmap(shard_id_base(S, 0)), PeerOut(), s0);
+    }
+    int rc = sharded_ensure_mailbox(S, std::min<int64_t>(nq, 1024) * k);
+    if (rc) return rc;
+    const int64_t chunk = std::max<int64_t>(1, S->mail_cap / k);
+    CB_REQUIRE(k <= S->mail_cap, "cb_sharded_search: k too large for the mailbox");
+    if (!q_host) {
+        DeviceGuard g(root->device);
+        CB_CUDA(cudaEventRecord(S->ev_q, s0));
+    }
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t m = std::min(chunk, nq - q0);
+        int slot0 = 0;
+        uint32_t total0 = 0;
+        for (int r = 0; r < R; r++) {
+            cb_index *ix = S->sh[r];
+            DeviceGuard g(ix->device);
+            cudaStream_t sr = r == 0 ? s0 : ix->stream;
+            const float *q = nullptr;
+            if (q_host) {
+                CB_CUDA(cudaMemcpyAsync(ix->d_q, q_host + q0 * kD, (size_t)m * kD * 4, cudaMemcpyHostToDevice, sr));
+                q = ix->d_q;
+            } else if (r == 0) {
+                q = q_dev0 + q0 * kD;
+            } else {
+                if (q0 == 0) CB_CUDA(cudaStreamWaitEvent(sr, S->ev_q, 0));
+                CB_CUDA(cudaMemcpyPeerAsync(ix->d_q, ix->device, q_dev0 + q0 * kD, root->device, (size_t)m * kD * 4, sr));
+                q = ix->d_q;
+            }
+            int slot = 0;
+            uint32_t total = 0;
+            rc = p2p_local_search(ix, m, q, k, shard_id_base(S, r), sr, &slot, &total);
+            if (rc) return rc;
+            if (r == 0) { slot0 = slot; total0 = total; }
+            else CB_CUDA(cudaEventRecord(S->ev_done[r], sr));
+        }
+        DeviceGuard g(root->device);
+        // one process: order the merge after every shard's kernels with events as well, so the merge
+        // blocks never spin beside kernels that still wait for an SM (shards may share a device)
+        for (int r = 1; r < R; r++) CB_CUDA(cudaStreamWaitEvent(s0, S->ev_done[r], 0));
+        if ((rc = p2p_root_merge(root, slot0, total0, m, k, D_dev0 + q0 * k, I_dev0 + q0 * k, s0))) return rc;
+    }
+    return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_sharded_create(int d, int storage_dtype, int ndev, const int *devices, cb_sharded **out) {
+    CB_REQUIRE(out != nullptr, "cb_sharded_create: out is null");
+    *out = nullptr;
+    CB_REQUIRE(ndev >= 1 && ndev <= kMaxRanks && devices, "cb_sharded_create: 1..%d devices", kMaxRanks);
+    cb_sharded *S = new (std::nothrow) cb_sharded();
+    if (!S) { set_error("out of host memory"); return CB_ERR_OOM; }
+    S->d = d;
+    S->dtype = storage_dtype;
+    for (int r = 0; r < ndev; r++) {
+        cb_index *ix = nullptr;
+        int rc = cb_flatip_create(d, storage_dtype, devices[r], &ix);
+        if (rc) { cb_sharded_free(S); return rc; }
+        S->sh.push_back(ix);
+        S->devices.push_back(devices[r]);
+    }
+    S->segs.resize(ndev);
+    S->ev_done.assign(ndev, nullptr);
+    // every shard's device must be able to store into the root device's memory
+    for (int r = 0; r < ndev; r++) {
+        DeviceGuard g(devices[r]);
+        cudaError_t e = cudaEventCreateWithFlags(&S->ev_done[r], cudaEventDisableTiming);
+        if (e == cudaSuccess && r == 0) e = cudaEventCreateWithFlags(&S->ev_q, cudaEventDisableTiming);
+        if (e == cudaSuccess && devices[r] != devices[0]) {
+            int can = 0;
+            e = cudaDeviceCanAccessPeer(&can, devices[r], devices[0]);
+            if (e == cudaSuccess && !can) {
+                set_error("cb_sharded_create: device %d cannot access device %d's memory (no NVLink/P2P path)", devices[r], devices[0]);
+                cb_sharded_free(S);
+                return CB_ERR_CUDA;
+            }
+            if (e == cudaSuccess) {
+                e = cudaDeviceEnablePeerAccess(devices[0], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            }
+        }
+        if (e != cudaSuccess) {
+            set_error("cb_sharded_create: %s", cudaGetErrorString(e));
+            cb_sharded_free(S);
+            return CB_ERR_CUDA;
+        }
+    }
+    *out = S;
+    return CB_OK;
+}
+
+void cb_sharded_free(cb_sharded *S) {
+    if (!S) return;
+    // shards 1.. point into the root's mailbox: drop those references before the root frees it
+    for (size_t r = 1; r < S->sh.size(); r++)
+        if (S->sh[r]) { DeviceGuard g(S->sh[r]->device); cudaStreamSynchronize(S->sh[r]->stream); S->sh[r]->p2p = P2P(); }
+    for (size_t r = 0; r < S->sh.size(); r++) {
+        if (r < S->ev_done.size() && S->ev_done[r]) { DeviceGuard g(S->devices[r]); cudaEventDestroy(S->ev_done[r]); }
+    }
+    if (S->ev_q) { DeviceGuard g(S->devices[0]); cudaEventDestroy(S->ev_q); }
+    for (cb_index *ix : S->sh) cb_flatip_free(ix);
+    delete S;
+}
+
+int64_t cb_sharded_ntotal(const cb_sharded *S) { return S ? S->ntotal : -1; }
+int cb_sharded_num_shards(const cb_sharded *S) { return S ? (int)S->sh.size() : -1; }
+cb_index *cb_sharded_shard(cb_sharded *S, int r) { return (S && r >= 0 && r < (int)S->sh.size()) ? S->sh[r] : nullptr; }
+
+int cb_sharded_reserve(cb_sharded *S, int64_t n_rows_total) {
+    CB_REQUIRE(S != nullptr, "cb_sharded_reserve: null index");
+    const int64_t R = (int64_t)S->sh.size(), per = (n_rows_total + R - 1) / R;
+    for (cb_index *ix : S->sh) {
+        int rc = cb_flatip_reserve(ix, per);
+        if (rc) return rc;
+    }
+    return CB_OK;
+}
+
+int cb_sharded_reset(cb_sharded *S) {
+    CB_REQUIRE(S != nullptr, "cb_sharded_reset: null index");
+    for (size_t r = 0; r < S->sh.size(); r++) {
+        int rc = cb_flatip_reset(S->sh[r]);
+        if (rc) return rc;
+        S->segs[r].clear();
+    }
+    S->ntotal = 0;
+    return CB_OK;
+}
+
+int cb_sharded_add(cb_sharded *S, int64_t n, const float *x_host) {
+    CB_REQUIRE(S != nullptr, "cb_sharded_add: null index");
+    CB_REQUIRE(n >= 0, "cb_sharded_add: n < 0");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(x_host != nullptr, "cb_sharded_add: null rows");
+    const int64_t R = (int64_t)S->sh.size(), per = (n + R - 1) / R;
+    for (int r = 0; r < (int)R; r++) {
+        const int64_t lo = std::min<int64_t>(r * per, n), hi = std::min<int64_t>((r + 1) * per, n);
+        if (hi <= lo) continue;
+        const int64_t local0 = S->sh[r]->ntotal;
+        int rc = cb_flatip_add(S->sh[r], hi - lo, x_host + lo * kD);
+        if (rc) return rc;
+        sharded_note_rows(S, r, local0, S->ntotal + lo, hi - lo);
+        if ((rc = sharded_sync_segments(S, r))) return rc;
+    }
+    S->ntotal += n;
+    return CB_OK;
+}
+
+int cb_sharded_add_device(cb_sharded *S, int shard, int64_t n, const void *x_dev, int src_dtype, void *stream) {
+    CB_REQUIRE(S != nullptr, "cb_sharded_add_device: null index");
+    CB_REQUIRE(shard >= 0 && shard < (int)S->sh.size(), "cb_sharded_add_device: shard %d out of range", shard);
+    if (n == 0) return CB_OK;
+    const int64_t local0 = S->sh[shard]->ntotal;
+    int rc = cb_flatip_add_device(S->sh[shard], n, x_dev, src_dtype, stream);
+    if (rc) return rc;
+    sharded_note_rows(S, shard, local0, S->ntotal, n);
+    if ((rc = sharded_sync_segments(S, shard))) return rc;
+    S->ntotal += n;
+    return CB_OK;
+}
+
+int cb_sharded_search_device(cb_sharded *S, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
+                             int64_t *I_dev, void *stream) {
+    CB_REQUIRE(S != nullptr, "cb_sharded_search_device: null index");
+    CB_REQUIRE(nq >= 0, "cb_sharded_search_device: nq < 0");
+    CB_REQUIRE(k > 0 && k < (1ll << 31), "cb_sharded_search_device: k must be in [1, 2^31) (got %lld)", (long long)k);
+    if (nq == 0) return CB_OK;
+    CB_REQUIRE(q_dev && D_dev && I_dev, "cb_sharded_search_device: null buffer");
+    for (size_t r = 1; r < S->sh.size(); r++) {
+        DeviceGuard g(S->sh[r]->device);
+        int rc = ensure_q(S->sh[r], std::min<int64_t>(nq, 1024));
+        if (rc) return rc;
+    }
+    return sharded_search_impl(S, nq, q_dev, nullptr, k, D_dev, I_dev, (cudaStream_t)stream);
+}
+
+int cb_sharded_search(cb_sharded *S, int64_t nq, const float *q_host, int64_t k, float *D_host, int64_t *I_host) {
+    CB_REQUIRE(S != nullptr, "cb_sharded_search: null index");
+    CB_REQUIRE(nq >= 0, "cb_sharded_search: nq < 0");
+    CB_REQUIRE(k > 0 && k < (1ll << 31), "cb_sharded_search: k must be > 0 (got %lld)", (long long)k);
+    if (nq == 0) return CB_OK;
+    CB_REQUIRE(q_host && D_host && I_host, "cb_sharded_search: null buffer");
+    cb_index *root = S->sh[0];
+    if (S->sh.size() == 1) return cb_flatip_search(root, nq, q_host, k, D_host, I_host);
+    int rc;
+    for (cb_index *ix : S->sh) {
+        DeviceGuard g(ix->device);
+        if ((rc = ensure_q(ix, nq))) return rc;
+    }
+    DeviceGuard g(root->device);
+    if ((rc = ensure_out(root, nq * k))) return rc;
+    memcpy(root->h_q, q_host, (size_t)nq * kD * 4);           // one pinned copy feeds every shard's H2D
+    rc = sharded_search_impl(S, nq, nullptr, root->h_q, k, root->d_D, root->d_I, root->stream);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(root->h_D, root->d_D, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, root->stream));
+    CB_CUDA(cudaMemcpyAsync(root->h_I, root->d_I, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, root->stream));
+    CB_CUDA(cudaStreamSynchronize(root->stream));
+    memcpy(D_host, root->h_D, (size_t)nq * k * 4);
+    memcpy(I_host, root->h_I, (size_t)nq * k * 8);
+    return CB_OK;
+}
+
+int cb_sharded_get_rows(cb_sharded *S, int64_t start, int64_t n, float *out_host) {
+    CB_REQUIRE(S != nullptr, "cb_sharded_get_rows: null index");
+    CB_REQUIRE(start >= 0 && n >= 0 && start + n <= S->ntotal, "cb_sharded_get_rows: range out of bounds");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(out_host != nullptr, "cb_sharded_get_rows: null buffer");
+    for (size_t r = 0; r < S->sh.size(); r++)
+        for (const auto &sg : S->segs[r]) {
+            const int64_t lo = std::max(sg.global, start), hi = std::min(sg.global + sg.count, start + n);
+            if (hi <= lo) continue;
+            int rc = cb_flatip_get_rows(S->sh[r], sg.local + (lo - sg.global), hi - lo, out_host + (lo - start) * kD);
+            if (rc) return rc;
+        }
     return CB_OK;
 }
 

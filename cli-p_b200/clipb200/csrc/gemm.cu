@@ -17,7 +17,7 @@
 // call sites /root/reference/build-index.py:49, query-index.py:108).
 //
 // Persistent kernel, one CTA per SM, static tile schedule (n fastest so concurrently
-// running CTAs share A tiles through L2).  Warp roles (192 threads):
+// running CTAs share A tiles through L2).  Warp roles (320 threads):
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
 //   warps 2..9  epilogue; warp w owns TMEM lanes 32*(w%4) .. +31 (= tile rows) and the
@@ -27,6 +27,9 @@
 #include "tc_ptx.cuh"
 
 #include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
 
 namespace cb {
 namespace {
@@ -78,7 +81,12 @@ template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g, const int m_tiles, const int n_tiles, const int stages_and_dbg) {
-    const int num_stages = stages_and_dbg & 0xff, dbg_mode = (stages_and_dbg >> 8) & 0xff, raster = stages_and_dbg >> 16;
+    const int num_stages = stages_and_dbg & 0xff, raster = stages_and_dbg >> 16;
+#ifdef CLIPB200_EXPERIMENTS
+    const int dbg_mode = (stages_and_dbg >> 8) & 0xff;     // result-corrupting perf probes (profiles/gemm_decompose.py)
+#else
+    constexpr int dbg_mode = 0;                            // compiled out of the product library
+#endif
     // tile -> (m tile, n tile).  raster 0: n fastest (concurrent CTAs share an A tile); 1: m fastest (share a
     // W tile); g >= 2: groups of g m-tiles, m fastest inside a group (share both)
     auto decode = [&](int tile, int &mt, int &nt) {
@@ -494,11 +502,13 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     auto kern = gemm_tcgen05_kernel<BN, EPI, NCTA>;
     int cur_dev = 0;
     CB_CUDA(cudaGetDevice(&cur_dev));
-    static bool attr_done[64] = {false};       // function attributes are per device
-    if (!attr_done[cur_dev & 63]) {
-        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_done[cur_dev & 63] = true;
-    }
+    // function attributes are per device; handles on different GPUs launch from different host threads
+    static std::once_flag attr_once[64];
+    cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once[cur_dev & 63], [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    });
+    CB_CUDA(attr_err);
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
     if (rc) return rc;
@@ -527,9 +537,11 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int stages = C::STAGES;
-    if (const char *e = getenv("CLIPB200_GEMM_STAGES")) stages = std::max(2, std::min(C::STAGES, atoi(e)));
-    if (const char *e = getenv("CLIPB200_GEMM_DEBUG")) stages |= atoi(e) << 8;   // perf experiments only
-    if (const char *e = getenv("CLIPB200_GEMM_RASTER")) stages |= atoi(e) << 16;
+    if (tune(T_GEMM_STAGES) > 0) stages = std::max(2, std::min(C::STAGES, (int)tune(T_GEMM_STAGES)));
+#ifdef CLIPB200_EXPERIMENTS
+    if (tune(T_GEMM_DEBUG) > 0) stages |= (int)tune(T_GEMM_DEBUG) << 8;
+#endif
+    if (tune(T_GEMM_RASTER) > 0) stages |= (int)tune(T_GEMM_RASTER) << 16;
     CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, m_tiles, n_tiles, stages));
     CB_LAUNCH_CHECK();
     return CB_OK;
@@ -605,12 +617,12 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
     int ncta = 1, bn = 128;
     pick_config(g.M, g.N, sms, &ncta, &bn);
     if (!g.stats_out) {      // test/experiment overrides (the stats layout depends on the default choice)
-        if (const char *e = getenv("CLIPB200_GEMM_BN")) {
-            int v = atoi(e);
+        if (tune(T_GEMM_BN) > 0) {
+            int v = (int)tune(T_GEMM_BN);
             if ((v == 128 || v == 192 || v == 256 || (v == 64 && ncta == 1)) && g.N % v == 0) bn = v;
         }
-        if (const char *e = getenv("CLIPB200_GEMM_NCTA")) {
-            int v = atoi(e);
+        if (tune(T_GEMM_NCTA) > 0) {
+            int v = (int)tune(T_GEMM_NCTA);
             if ((v == 1 || (v == 2 && g.M > BM)) && !(v == 2 && bn == 64)) ncta = v;
         }
     }

@@ -260,7 +260,7 @@ int layernorm_f16(const __half *in, __half *out, const float *gamma, const float
     CB_REQUIRE(width == 768 || width == 512, "layernorm_f16: width %d not supported", width);
     if (rows == 0) return CB_OK;
     int per_sm = 6;
-    if (const char *e = getenv("CLIPB200_LN_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));
+    if (tune(T_LN_BLOCKS_PER_SM) > 0) per_sm = (int)tune(T_LN_BLOCKS_PER_SM);
     const int grid = std::min((rows + 7) / 8, kNumSMs * per_sm);
     if (cls_period <= 0) cls_period = 1;
     if (width == 768)

@@ -56,23 +56,11 @@ def _as_f32_2d(x, d: int, what: str) -> np.ndarray:
 
 
 class _Shard:
-    """One device-resident shard = one cb_index handle."""
+    """Borrowed view of one device-resident shard (a cb_index handle owned by the cb_sharded)."""
 
-    def __init__(self, d: int, storage: int, device: int):
-        self.handle = C.c_void_p()
-        N.check(N.lib().cb_flatip_create(d, storage, device, C.byref(self.handle)))
+    def __init__(self, handle, device: int):
+        self.handle = handle
         self.device = device
-
-    def close(self):
-        if getattr(self, "handle", None):
-            N.lib().cb_flatip_free(self.handle)
-            self.handle = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
 
     @property
     def ntotal(self) -> int:
@@ -84,8 +72,10 @@ class IndexFlatIP:
 
     devices: CUDA ordinals holding the shards.  One device (default: the current
     torch device if torch is imported and CUDA is initialised, else 0) gives the
-    plain single-GPU index.  Several devices shard every add() call contiguously
-    and merge per-device top-k on devices[0].
+    plain single-GPU index.  Several devices shard every add() call contiguously;
+    a search is ONE C call (cb_sharded_search): the query fans out, every device
+    runs its kernel chain and stores its top-k into a mailbox in devices[0]'s
+    memory over NVLink, and devices[0] merges (include/clipb200.h, cb_sharded_*).
     """
 
     def __init__(self, d: int = 512, storage=None, devices: Optional[Sequence[int]] = None):
@@ -97,17 +87,30 @@ class IndexFlatIP:
         if devices is None:
             env = os.environ.get("CLIPB200_DEVICES")
             devices = [int(t) for t in env.split(",")] if env else [_default_device()]
-        self._devices = list(devices)
+        self._devices = [int(t) for t in devices]
         assert len(self._devices) >= 1
-        self._shards: List[_Shard] = [_Shard(self.d, self._storage, dev) for dev in self._devices]
-        # multi-device bookkeeping: per shard, segments (local_start, global_start, count)
-        self._segments: List[List[tuple]] = [[] for _ in self._devices]
-        self._ntotal = 0
+        self._handle = C.c_void_p()
+        arr = (C.c_int * len(self._devices))(*self._devices)
+        N.check(N.lib().cb_sharded_create(self.d, self._storage, len(self._devices), arr, C.byref(self._handle)))
+        self._shards: List[_Shard] = [
+            _Shard(C.c_void_p(N.lib().cb_sharded_shard(self._handle, r)), dev) for r, dev in enumerate(self._devices)]
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            N.lib().cb_sharded_free(self._handle)
+            self._handle = None
+            self._shards = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # -- faiss attributes ------------------------------------------------------
     @property
     def ntotal(self) -> int:
-        return self._ntotal
+        return int(N.lib().cb_sharded_ntotal(self._handle))
 
     @property
     def storage(self) -> str:
@@ -117,54 +120,29 @@ class IndexFlatIP:
         _as_f32_2d(x, self.d, "train")
 
     def reset(self) -> None:
-        for sh in self._shards:
-            N.check(N.lib().cb_flatip_reset(sh.handle))
-        self._segments = [[] for _ in self._devices]
-        self._ntotal = 0
+        N.check(N.lib().cb_sharded_reset(self._handle))
 
     def reserve(self, n: int) -> None:
-        per = -(-int(n) // len(self._shards))
-        for sh in self._shards:
-            N.check(N.lib().cb_flatip_reserve(sh.handle, per))
+        N.check(N.lib().cb_sharded_reserve(self._handle, int(n)))
 
     # -- add -------------------------------------------------------------------
     def add(self, x) -> None:
         x = _as_f32_2d(x, self.d, "add")
-        n = x.shape[0]
-        if n == 0:
-            return
-        R = len(self._shards)
-        if R == 1:
-            N.check(N.lib().cb_flatip_add(self._shards[0].handle, n, x.ctypes.data_as(C.c_void_p)))
-        else:
-            per = -(-n // R)
-            for r, sh in enumerate(self._shards):
-                lo, hi = min(r * per, n), min((r + 1) * per, n)
-                if hi <= lo:
-                    continue
-                part = x[lo:hi]
-                local0 = sh.ntotal
-                N.check(N.lib().cb_flatip_add(sh.handle, hi - lo, part.ctypes.data_as(C.c_void_p)))
-                self._segments[r].append((local0, self._ntotal + lo, hi - lo))
-        self._ntotal += n
+        if x.shape[0]:
+            N.check(N.lib().cb_sharded_add(self._handle, x.shape[0], x.ctypes.data_as(C.c_void_p)))
 
     def add_device(self, x_dev, shard: int = 0) -> None:
-        """Append rows already on the GPU (torch CUDA tensor, fp16 or fp32, (n, d))."""
+        """Append rows already on the GPU (torch CUDA tensor, fp16 or fp32, (n, d)) to one shard;
+        they get the next n ids."""
         import torch
         assert x_dev.is_cuda and x_dev.dim() == 2 and x_dev.shape[1] == self.d
         assert x_dev.dtype in (torch.float16, torch.float32)
         x_dev = x_dev.contiguous()
-        sh = self._shards[shard]
-        assert x_dev.device.index == sh.device
-        n = x_dev.shape[0]
+        assert x_dev.device.index == self._devices[shard]
         src = N.CB_F16 if x_dev.dtype == torch.float16 else N.CB_F32
         stream = torch.cuda.current_stream(x_dev.device).cuda_stream
-        local0 = sh.ntotal
-        N.check(N.lib().cb_flatip_add_device(sh.handle, n, C.c_void_p(x_dev.data_ptr()), src,
-                                             C.c_void_p(stream)))
-        if len(self._shards) > 1:
-            self._segments[shard].append((local0, self._ntotal, n))
-        self._ntotal += n
+        N.check(N.lib().cb_sharded_add_device(self._handle, shard, x_dev.shape[0], C.c_void_p(x_dev.data_ptr()), src,
+                                              C.c_void_p(stream)))
 
     # -- search ----------------------------------------------------------------
     def search(self, x, k: int):
@@ -174,17 +152,9 @@ class IndexFlatIP:
         nq = x.shape[0]
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
-        if nq == 0:
-            return D, I
-        if len(self._shards) == 1:
-            N.check(N.lib().cb_flatip_search(self._shards[0].handle, nq, x.ctypes.data_as(C.c_void_p), k,
-                                             D.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p)))
-            return D, I
-        import torch
-        q = torch.from_numpy(x)
-        Dt, It = self.search_device(q, k)
-        D[...] = Dt.cpu().numpy()
-        I[...] = It.cpu().numpy()
+        if nq:
+            N.check(N.lib().cb_sharded_search(self._handle, nq, x.ctypes.data_as(C.c_void_p), k,
+                                              D.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p)))
         return D, I
 
     def search_device(self, q, k: int):
@@ -194,58 +164,26 @@ class IndexFlatIP:
         k = int(k)
         assert k > 0
         nq = q.shape[0]
-        R = len(self._shards)
         dev0 = torch.device("cuda", self._devices[0])
-        outs = []
-        for r, sh in enumerate(self._shards):
-            dev = torch.device("cuda", sh.device)
-            with torch.cuda.device(dev):
-                qd = q.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-                Dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
-                Id = torch.empty((nq, k), dtype=torch.int64, device=dev)
-                stream = torch.cuda.current_stream(dev).cuda_stream
-                N.check(N.lib().cb_flatip_search_device(
-                    sh.handle, nq, C.c_void_p(qd.data_ptr()), k, C.c_void_p(Dd.data_ptr()),
-                    C.c_void_p(Id.data_ptr()), 0, C.c_void_p(stream)))
-                if R > 1:
-                    Id = self._local_to_global(r, Id)
-                outs.append((Dd, Id))
-        if R == 1:
-            return outs[0]
         with torch.cuda.device(dev0):
-            Dall = torch.stack([d.to(dev0, non_blocking=True) for d, _ in outs])
-            Iall = torch.stack([i.to(dev0, non_blocking=True) for _, i in outs])
-            return merge_topk_device(Dall, Iall, k)
-
-    def _local_to_global(self, r: int, I_local):
-        import torch
-        segs = self._segments[r]
-        if not segs:
-            return I_local
-        dev = I_local.device
-        starts = torch.tensor([s[0] for s in segs], dtype=torch.int64, device=dev)
-        gstarts = torch.tensor([s[1] for s in segs], dtype=torch.int64, device=dev)
-        idx = torch.bucketize(I_local.clamp_min(0), starts, right=True) - 1
-        out = I_local - starts[idx] + gstarts[idx]
-        return torch.where(I_local < 0, I_local, out)
+            qd = q.to(device=dev0, dtype=torch.float32, non_blocking=True).contiguous()
+            D = torch.empty((nq, k), dtype=torch.float32, device=dev0)
+            I = torch.empty((nq, k), dtype=torch.int64, device=dev0)
+            stream = torch.cuda.current_stream(dev0).cuda_stream
+            N.check(N.lib().cb_sharded_search_device(self._handle, nq, C.c_void_p(qd.data_ptr()), k,
+                                                     C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
+                                                     C.c_void_p(stream)))
+            qd.record_stream(torch.cuda.current_stream(dev0))
+        return D, I
 
     # -- reconstruct -------------------------------------------------------------
     def reconstruct_n(self, n0: int = 0, ni: int = -1) -> np.ndarray:
         if ni < 0:
-            ni = self._ntotal - n0
-        assert 0 <= n0 and n0 + ni <= self._ntotal
+            ni = self.ntotal - n0
+        assert 0 <= n0 and n0 + ni <= self.ntotal
         out = np.empty((ni, self.d), dtype=np.float32)
-        if len(self._shards) == 1:
-            N.check(N.lib().cb_flatip_get_rows(self._shards[0].handle, n0, ni, out.ctypes.data_as(C.c_void_p)))
-            return out
-        for r, sh in enumerate(self._shards):
-            for (l0, g0, cnt) in self._segments[r]:
-                lo, hi = max(g0, n0), min(g0 + cnt, n0 + ni)
-                if hi <= lo:
-                    continue
-                tmp = np.empty((hi - lo, self.d), dtype=np.float32)
-                N.check(N.lib().cb_flatip_get_rows(sh.handle, l0 + (lo - g0), hi - lo, tmp.ctypes.data_as(C.c_void_p)))
-                out[lo - n0:hi - n0] = tmp
+        if ni:
+            N.check(N.lib().cb_sharded_get_rows(self._handle, n0, ni, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def reconstruct(self, i: int) -> np.ndarray:
@@ -264,13 +202,14 @@ class IndexIVFFlat:
         assert isinstance(quantizer, IndexFlatIP), "quantizer must be an IndexFlatIP"
         assert metric == METRIC_INNER_PRODUCT, "only METRIC_INNER_PRODUCT is supported"
         assert int(d) == quantizer.d
-        self.quantizer = quantizer
+        self.quantizer = quantizer       # stays empty, as faiss's coarse quantizer would before train()
         self.d = int(d)
         self.nlist = int(nlist)
         self.nprobe = 1
         self.metric_type = metric
         self.is_trained = False
-        self._flat = quantizer   # the quantizer object doubles as the row store
+        # the rows live in a flat store of the IVF's own, on the quantizer's devices / storage dtype
+        self._flat = IndexFlatIP(self.d, storage=quantizer._storage, devices=quantizer._devices)
 
     @property
     def ntotal(self) -> int:
@@ -348,9 +287,11 @@ def read_index(path: str, storage=None, devices: Optional[Sequence[int]] = None)
         flat.add(rows)
     kind, nlist, nprobe = (1 if parsed.kind == "ivf" else 0), parsed.nlist, parsed.nprobe
     if kind == 1:
-        ivf = IndexIVFFlat(flat, flat.d, nlist, METRIC_INNER_PRODUCT)
+        ivf = IndexIVFFlat.__new__(IndexIVFFlat)
+        ivf.quantizer = IndexFlatIP(parsed.d, storage=storage, devices=devices)
+        ivf.d, ivf.nlist, ivf.nprobe, ivf.metric_type = flat.d, nlist, nprobe, METRIC_INNER_PRODUCT
         ivf.is_trained = True
-        ivf.nprobe = nprobe
+        ivf._flat = flat
         return ivf
     return flat
 

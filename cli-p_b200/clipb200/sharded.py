@@ -2,10 +2,10 @@
 
 Rows are split contiguously: rank r owns global ids [base_r, base_r + n_r).  A
 query batch is replicated (2 KB/query), every rank scans its own shard and
-produces a sorted local top-k with GLOBAL ids, then ONE collective moves the
-per-rank results (each rank's D block and I block packed back to back in one
-byte buffer) and the merge kernel picks the global top-k by (-score, id), which
-makes the answer bit-identical to the single-GPU answer.
+produces a sorted local top-k with GLOBAL ids, then the per-rank results travel ONCE
+(by peer stores into rank 0's mailbox, or by one collective of the packed D | I blocks)
+and the merge kernel picks the global top-k by (-score, id), which makes the answer
+bit-identical to the single-GPU answer.
 
 torch.distributed is plumbing here (NCCL over NVLink on the GPU box, gloo in the
 CPU tests); `local_search` / `merge` are injectable so the host logic can be
@@ -36,9 +36,20 @@ def packed_bytes(nq: int, k: int) -> Tuple[int, int]:
 
 
 class DistributedFlatIP:
+    """One rank's view of the sharded index.
+
+    transport "p2p" (default on GPUs): the per-rank top-k lists are stored straight into a mailbox
+    in rank 0's HBM over NVLink by the kernel that produces them, and rank 0's merge kernel waits on
+    per-rank counters (include/clipb200.h, cb_flatip_*_p2p_*): one kernel chain per GPU, no
+    collective, no Python between scan and answer.  The answer exists on rank 0 only.
+    transport "nccl": ONE all_gather_into_tensor of the packed per-rank results, then the merge
+    kernel on every rank (also the CPU/gloo test path, with injected local_search / merge).
+    """
+
     def __init__(self, index=None, group=None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, transport: Optional[str] = None,
+                 mailbox_elems: int = 128 * 1024):
         self.index = index
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -50,33 +61,63 @@ class DistributedFlatIP:
         self.ntotal_global = 0
         self._buf = None
         self._gather = None
-        # Opt-in (CLIPB200_SEARCH_GRAPHS=1): replay small-nq searches as one CUDA graph per (nq, k).
-        # Single-GPU gain is small (1.533 -> 1.529 ms); with NCCL inside the capture a 2-rank run
-        # hung in round 1, so it is restricted to world == 1 until that is understood.
-        self.use_graphs = os.environ.get("CLIPB200_SEARCH_GRAPHS", "0") == "1" and self.world == 1
-        self._graphs = {}
+        if transport is None:
+            transport = os.environ.get("CLIPB200_SEARCH_TRANSPORT", "p2p")
+        if local_search is not None or self.device.type != "cuda":
+            transport = "nccl"            # injected CPU stand-ins: the collective path (gloo in the tests)
+        assert transport in ("p2p", "nccl"), transport
+        self.transport = transport
+        self.mailbox_elems = int(mailbox_elems)
+        self._p2p_ready = False
 
     # ---- ingest ------------------------------------------------------------------
     def finalize(self, n_local: Optional[int] = None) -> None:
-        """Exchange shard sizes once so every rank knows its global id base."""
+        """Exchange shard sizes once so every rank knows its global id base; with the p2p
+        transport also map rank 0's mailbox into every rank (cudaIpc handle, exchanged once)."""
         if n_local is None:
             n_local = self.index.ntotal
         if self.world == 1:
             self.id_base, self.ntotal_global = 0, n_local
-            return
-        t = torch.tensor([n_local], dtype=torch.int64, device=self.device)
-        sizes = [torch.zeros_like(t) for _ in range(self.world)]
-        dist.all_gather(sizes, t, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
-        self.id_base = sum(sizes[:self.rank])
-        self.ntotal_global = sum(sizes)
+        else:
+            t = torch.tensor([n_local], dtype=torch.int64, device=self._plumbing_device())
+            sizes = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(sizes, t, group=self.group)
+            sizes = [int(s.item()) for s in sizes]
+            self.id_base = sum(sizes[:self.rank])
+            self.ntotal_global = sum(sizes)
+        if self.transport == "p2p" and self.world > 1 and not self._p2p_ready:
+            self._p2p_attach()
+
+    def _handle(self):
+        return self.index._shards[0].handle
+
+    def _plumbing_device(self):
+        """Where the few bytes of set-up traffic live: NCCL moves CUDA tensors, gloo CPU tensors."""
+        return self.device if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+
+    def _p2p_attach(self) -> None:
+        from . import _native as N
+        raw = (C.c_ubyte * 64)()
+        N.check(N.lib().cb_flatip_p2p_init(self._handle(), self.rank, self.world, self.mailbox_elems, raw))
+        h = torch.tensor(list(raw), dtype=torch.uint8, device=self._plumbing_device())
+        dist.broadcast(h, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        raw_root = (C.c_ubyte * 64)(*h.cpu().tolist())
+        N.check(N.lib().cb_flatip_p2p_connect(self._handle(), raw_root))
+        dist.barrier(group=self.group)          # nobody searches before every rank has mapped the mailbox
+        self._p2p_ready = True
+
+    def p2p_error(self) -> int:
+        """Sticky mailbox error flag (a peer did not deliver in time).  Synchronises."""
+        from . import _native as N
+        e = C.c_int(0)
+        N.check(N.lib().cb_flatip_p2p_status(self._handle(), C.byref(e)))
+        return int(e.value)
 
     # ---- search --------------------------------------------------------------------
     def _native_search(self, q, k, D, I, id_base):
         from . import _native as N
-        sh = self.index._shards[0]
         stream = torch.cuda.current_stream(q.device).cuda_stream
-        N.check(N.lib().cb_flatip_search_device(sh.handle, q.shape[0], C.c_void_p(q.data_ptr()), k,
+        N.check(N.lib().cb_flatip_search_device(self._handle(), q.shape[0], C.c_void_p(q.data_ptr()), k,
                                                 C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
                                                 id_base, C.c_void_p(stream)))
 
@@ -96,60 +137,40 @@ class DistributedFlatIP:
 
     def search(self, q: torch.Tensor, k: int):
         """q: (nq, d) float32 on this rank's device, identical on all ranks.
-        Returns (D, I) on every rank."""
+        Returns (D, I): on every rank with the nccl transport, on rank 0 only (None, None
+        elsewhere) with the p2p transport."""
         nq = q.shape[0]
-        if (self.use_graphs and q.is_cuda and nq < 16 and self._local_search == self._native_search
-                and self.ntotal_global > 0):
-            out = self._search_graphed(q, k)
-            if out is not None:
-                return out
-        return self._search_eager(q, k)
+        if self.world == 1:
+            D = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            self._local_search(q, k, D, I, self.id_base)
+            return D, I
+        if self.transport == "p2p":
+            return self._search_p2p(q, k)
+        return self._search_collective(q, k)
 
-    def _search_graphed(self, q: torch.Tensor, k: int):
-        key = (q.shape[0], k, q.shape[1])
-        ent = self._graphs.get(key)
-        if ent is None:
-            try:
-                q_static = torch.empty_like(q)
-                q_static.copy_(q)
-                for _ in range(2):                      # warm up: workspace allocation, func attributes, NCCL
-                    self._search_eager(q_static, k)
-                torch.cuda.synchronize(q.device)
-                # the graph owns its packed result / gather buffers (the eager ones are re-sized freely)
-                off_I, total = packed_bytes(q.shape[0], k)
-                bufs = (torch.empty(total, dtype=torch.uint8, device=self.device),
-                        torch.empty(total * self.world, dtype=torch.uint8, device=self.device))
-                self._search_eager(q_static, k, bufs)
-                torch.cuda.synchronize(q.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    D, I = self._search_eager(q_static, k, bufs)
-                ent = (g, q_static, D, I, bufs)
-            except Exception as e:                      # capture not possible here: stay eager, say so once
-                import sys
-                print(f"clipb200: CUDA-graph capture of the sharded search failed ({e}); running eagerly",
-                      file=sys.stderr)
-                self.use_graphs = False
-                return None
-            self._graphs[key] = ent
-        g, q_static, D, I = ent[:4]
-        q_static.copy_(q)
-        g.replay()
-        return D, I          # graph-owned outputs: valid until the next search with the same (nq, k)
-
-    def _search_eager(self, q: torch.Tensor, k: int, bufs=None):
+    def _search_p2p(self, q: torch.Tensor, k: int):
+        from . import _native as N
+        assert self._p2p_ready, "call finalize() first"
         nq = q.shape[0]
-        if bufs is None:
-            off_I, total = self._buffers(nq, k)
-            buf, gather = self._buf, self._gather
-        else:
-            off_I, total = packed_bytes(nq, k)
-            buf, gather = bufs
+        D = I = None
+        dp = ip = None
+        if self.rank == 0:
+            D = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            dp, ip = C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr())
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        N.check(N.lib().cb_flatip_search_p2p_device(self._handle(), nq, C.c_void_p(q.data_ptr()), k, dp, ip,
+                                                    self.id_base, C.c_void_p(stream)))
+        return D, I
+
+    def _search_collective(self, q: torch.Tensor, k: int):
+        nq = q.shape[0]
+        off_I, total = self._buffers(nq, k)
+        buf, gather = self._buf, self._gather
         D = buf[:nq * k * 4].view(torch.float32).view(nq, k)
         I = buf[off_I:].view(torch.int64).view(nq, k)
         self._local_search(q, k, D, I, self.id_base)
-        if self.world == 1:
-            return D.clone(), I.clone()
         if gather.is_cuda:
             dist.all_gather_into_tensor(gather, buf, group=self.group)
         else:  # gloo (CPU tests)

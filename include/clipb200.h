@@ -41,6 +41,18 @@ const char *cb_last_error(void);
 int cb_abi_version(void);
 int cb_device_count(int *n);
 
+/* Process-wide tuning knobs (tests, profiling).  Each knob is read ONCE from the environment variable
+ * CLIPB200_<NAME IN CAPITALS> when the library is loaded; launch paths never call getenv.  -1 = default.
+ *   gemm_bn, gemm_ncta, gemm_stages, gemm_raster   tcgen05 GEMM tile shape / ring depth / tile order
+ *   batch_min_nq       smallest query batch served by the tensor-core search (default 3 on shards of
+ *                      >= 1M rows, 16 below)
+ *   no_graph           1: small encode_* calls are never replayed as CUDA graphs
+ *   ln_blocks_per_sm   LayerNorm grid size
+ *   ln_fold            0 / 1 / unset: see cb_clip_finalize
+ * Result-corrupting perf probes (gemm_debug, skip) exist only in -DCLIPB200_EXPERIMENTS builds. */
+int cb_tuning_set(const char *name, int64_t value);
+int cb_tuning_get(const char *name, int64_t *value);
+
 /* ---- exact inner-product index (replaces faiss.IndexFlatIP) ----------- */
 
 /* faiss.IndexFlatIP(512)                       build-index.py:80
@@ -54,6 +66,7 @@ void cb_flatip_free(cb_index *ix);
 int64_t cb_flatip_ntotal(const cb_index *ix);
 int cb_flatip_dim(const cb_index *ix);
 int cb_flatip_storage_dtype(const cb_index *ix);
+int cb_flatip_device(const cb_index *ix);
 
 /* pre-size the shard (optional; add() grows geometrically otherwise) */
 int cb_flatip_reserve(cb_index *ix, int64_t n_rows);
@@ -61,6 +74,9 @@ int cb_flatip_reserve(cb_index *ix, int64_t n_rows);
 /* index.add(float32[n,512])                    build-index.py:99,107
  * rows are appended; ids are implicit and sequential from ntotal. */
 int cb_flatip_add(cb_index *ix, int64_t n, const float *x_host);
+/* rows already on the shard's device; queued on `stream`.  The index's own stream (the one the
+ * host-pointer entry points run on) is ordered after the add.  Calls that touch one index from
+ * several streams (add_device / search_device) must be ordered by the caller. */
 int cb_flatip_add_device(cb_index *ix, int64_t n, const void *x_dev, int src_dtype,
                          void *stream);
 
@@ -76,12 +92,14 @@ int cb_flatip_search(cb_index *ix, int64_t nq, const float *q_host, int64_t k,
 int cb_flatip_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k,
                             float *D_dev, int64_t *I_dev, int64_t id_base, void *stream);
 
-/* search dispatch: nq < 16 (or fp32 storage, or k > 1024) streams the shard once per
- * 4 queries (HBM-bound scan); larger batches on fp16 shards run the tcgen05 GEMM
- * with a fused per-query threshold filter (tensor-bound; synchronises the stream
- * once to read its overflow flag and falls back to the scan path if a candidate
- * list overflowed).  Counters for tests / benches: */
-int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_overflow_fallbacks);
+/* search dispatch: one or two queries (or fp32 storage, or k > 1024, or a shard under 8192 rows)
+ * stream the shard once per 4 queries (HBM-bound scan); larger batches on fp16 shards run a tcgen05
+ * GEMM of the fp16-rounded queries with a fused per-query threshold filter, then re-score the
+ * survivors exactly in fp32 (tensor-bound; flatip_batch.cu).  Both paths give the same answer bit
+ * for bit and neither synchronises.  Counters for tests / benches: batch searches served by the
+ * tensor-core path, and (query, row range) pairs whose candidate list overflowed and were
+ * re-selected exactly on the device (adversarial row order; this call synchronises). */
+int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_rescued);
 
 /* Merge R per-shard results into [nq][k] by (-score, id); ids < 0 are padding.
  * Shard r's block [nq][k] starts at D_in + r*shard_stride_D (elements) and
@@ -92,6 +110,46 @@ int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_ov
 int cb_topk_merge_device(int R, int64_t nq, int64_t k, const float *D_in,
                          const int64_t *I_in, int64_t shard_stride_D, int64_t shard_stride_I,
                          float *D_out, int64_t *I_out, void *stream);
+
+/* ---- the database sharded over GPUs --------------------------------------------
+ * Rows are split over the shards; a query is replicated, every shard selects its local top-k with
+ * GLOBAL ids, and the block that finishes a query's list stores it straight into a mailbox in the
+ * ROOT GPU's memory over NVLink (peer stores + a system-scope release on a per-rank counter).  The
+ * root's merge kernel acquires the counters and merges by (-score, id): one kernel chain per GPU,
+ * no collective, no host round trip, bit-identical to the unsharded answer.
+ *
+ * (1) one process per GPU (torchrun): every rank owns a cb_index; rank 0 allocates the mailbox and
+ *     publishes its cudaIpc handle, the others open it. */
+int cb_flatip_p2p_init(cb_index *ix, int rank, int world, int64_t max_elems, void *ipc_handle_out64);
+int cb_flatip_p2p_connect(cb_index *ix, const void *root_ipc_handle64);
+/* every rank calls this with the same (nq, k) sequence and the same queries; (D, I) are written on
+ * rank 0 only (may be NULL elsewhere).  id_base = the shard's first global row.  nq*k is chunked to
+ * max_elems per mailbox slot; k <= max_elems. */
+int cb_flatip_search_p2p_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
+                                int64_t *I_dev, int64_t id_base, void *stream);
+/* sticky error flag of the mailbox (a peer did not deliver within 20 s); synchronises */
+int cb_flatip_p2p_status(cb_index *ix, int *error);
+
+/* (2) ONE process driving several GPUs -- the REPL of query-index.py:29-30,111 with
+ *     faiss.IndexFlatIP(devices=[...]): the same protocol between the devices of this process. */
+typedef struct cb_sharded cb_sharded;
+int cb_sharded_create(int d, int storage_dtype, int ndev, const int *devices, cb_sharded **out);
+void cb_sharded_free(cb_sharded *s);
+int64_t cb_sharded_ntotal(const cb_sharded *s);
+int cb_sharded_num_shards(const cb_sharded *s);
+cb_index *cb_sharded_shard(cb_sharded *s, int r);          /* borrowed: stats, timing, device rows */
+int cb_sharded_reserve(cb_sharded *s, int64_t n_rows_total);
+int cb_sharded_reset(cb_sharded *s);
+/* index.add: the n rows get the next n ids and are split contiguously over the shards */
+int cb_sharded_add(cb_sharded *s, int64_t n, const float *x_host);
+/* rows already on shard `shard`'s device get the next n ids */
+int cb_sharded_add_device(cb_sharded *s, int shard, int64_t n, const void *x_dev, int src_dtype, void *stream);
+/* index.search: one call fans the query out, every device runs its chain, the root merges */
+int cb_sharded_search(cb_sharded *s, int64_t nq, const float *q_host, int64_t k, float *D_host, int64_t *I_host);
+/* q, D, I on devices[0]; `stream` is a stream of devices[0]; never synchronises */
+int cb_sharded_search_device(cb_sharded *s, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
+                             int64_t *I_dev, void *stream);
+int cb_sharded_get_rows(cb_sharded *s, int64_t start, int64_t n, float *out_host);
 
 /* copy rows [start, start+n) back to the host as float32 (index.reconstruct_n;
  * used by write_index, build-index.py:109) */
@@ -124,6 +182,11 @@ int cb_clip_create(int device, int max_image_batch, int max_text_batch, cb_clip 
 int cb_clip_set_param(cb_clip *m, const char *name, const float *data_host, int64_t numel);
 int cb_clip_finalize(cb_clip *m);
 void cb_clip_free(cb_clip *m);
+/* ln_1 / ln_2 are folded into the QKV / c_fc GEMMs (gamma in the weights, row statistics from the
+ * previous epilogue).  With the ln_fold knob unset, cb_clip_finalize runs a small calibration batch
+ * through both forms and keeps the fold only if the embeddings agree to cosine >= 0.9998; otherwise
+ * LayerNorm stays a separate fp32 launch, as in the reference.  Reports the decision. */
+int cb_clip_ln_fold_status(cb_clip *m, int *folded, double *min_cosine);
 
 /* image_features = model.encode_image(image)            build-index.py:49
  * (+ `/ image_features.norm(dim=-1, keepdim=True)`      build-index.py:50  when normalize != 0)

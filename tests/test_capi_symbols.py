@@ -72,6 +72,35 @@ def test_sass_is_sm100(lib):
     assert "sm_100a" in out
 
 
+def test_tensor_core_kernels_are_tcgen05_tma_tmem(lib):
+    """The GEMM and batch-search kernels must really be Blackwell tensor-core code: tcgen05.mma
+    (UTCHMMA), TMA loads (UTMALDG), TMEM reads (LDTM), and TMA bulk stores (UTMASTG) in the GEMM
+    epilogues that store fp16 tiles.  profiles/r02_sass_digest.txt is this table, committed."""
+    import importlib.util
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    spec = importlib.util.spec_from_file_location("sass_digest", os.path.join(ROOT, "profiles", "sass_digest.py"))
+    sd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sd)
+    d = sd.digest()
+    names = sd.demangle(list(d))
+    tc = {sd.shorten(names[k]): c for k, c in d.items()
+          if "gemm_tcgen05_kernel" in names[k] or "flatip_batch_kernel" in names[k]}
+    assert len([k for k in tc if k.startswith("gemm_tcgen05_kernel")]) >= 20      # BN x epilogue x NCTA
+    assert {"flatip_batch_kernel<1>", "flatip_batch_kernel<2>"} <= set(tc)
+    for k, c in tc.items():
+        assert c["UTCHMMA"] >= 4 and c["UTMALDG"] >= 2 and c["LDTM"] >= 1 and c["UTCBAR"] >= 2, (k, dict(c))
+        assert c["HMMA"] == 0, f"{k} fell back to legacy mma.sync"
+    stores = [c["UTMASTG"] for k, c in tc.items() if k.startswith("gemm_tcgen05_kernel")]
+    assert sum(1 for x in stores if x >= 1) >= 12
+    # the debug probes are compiled out of the product library
+    from clipb200 import _native
+    assert _native.lib().cb_tuning_set(b"gemm_debug", 1) == _native.CB_ERR_INVALID
+    assert _native.lib().cb_tuning_set(b"skip", 1) == _native.CB_ERR_INVALID
+    assert _native.lib().cb_tuning_set(b"gemm_bn", -1) == _native.CB_OK
+
+
 def test_reference_import_lines_resolve_to_clipb200():
     """`import lmdb, clip, faiss` (build-index.py:5-8, query-index.py:6-9) with cli-p_b200/ first on
     PYTHONPATH must bind to this package, in a fresh interpreter, without a GPU."""

@@ -246,6 +246,10 @@ def test_clip_load_surface(monkeypatch):
     from PIL import Image
     from clipb200 import clip
     monkeypatch.delenv("CLIP_WEIGHTS", raising=False)
+    monkeypatch.delenv("CLIPB200_SYNTHETIC_WEIGHTS", raising=False)
+    with pytest.raises(RuntimeError, match="CLIP_WEIGHTS"):
+        clip.load("ViT-B/32", device="cuda", jit=False)     # never silently embeds with random weights
+    monkeypatch.setenv("CLIPB200_SYNTHETIC_WEIGHTS", "1")
     model, transform = clip.load("ViT-B/32", device="cuda", jit=False, max_image_batch=4, max_text_batch=2)
     model.eval()
     rng = np.random.default_rng(0)
@@ -300,17 +304,20 @@ def test_pipelined_submit_equals_blocking_call(model, golden_inputs):
         assert np.array_equal(o.numpy(), ref)
 
 
-def test_folded_and_unfolded_layernorm_agree(sd, golden_inputs, monkeypatch):
-    """Default: ln_1/ln_2 folded into the QKV / c_fc GEMMs.  CLIPB200_NO_LN_FOLD=1 keeps separate
-    LayerNorm launches; both must agree with each other and with the oracle."""
+def test_folded_and_unfolded_layernorm_agree(sd, golden_inputs):
+    """Default: ln_1/ln_2 folded into the QKV / c_fc GEMMs after a calibration batch agreed with the
+    unfolded form.  The ln_fold knob = 0 keeps separate LayerNorm launches; both must agree with each
+    other and with the oracle."""
     import torch
-    from clipb200 import clip
+    from clipb200 import _native, clip
     from oracle import clip_ref
     images, tokens, _ = golden_inputs
     folded = clip.CLIPB200(sd, device=0, max_image_batch=4, max_text_batch=4)
-    monkeypatch.setenv("CLIPB200_NO_LN_FOLD", "1")
-    plain = clip.CLIPB200(sd, device=0, max_image_batch=4, max_text_batch=4)
-    monkeypatch.delenv("CLIPB200_NO_LN_FOLD")
+    is_folded, cal_cos = folded.ln_fold_status()
+    assert is_folded and cal_cos >= 0.9998, (is_folded, cal_cos)
+    with _native.tuning(ln_fold=0):
+        plain = clip.CLIPB200(sd, device=0, max_image_batch=4, max_text_batch=4)
+    assert plain.ln_fold_status() == (False, -2.0)
     a, b = folded.encode_image(images.cuda()), plain.encode_image(images.cuda())
     assert _cos(torch, a, b) >= 0.99995
     ref = clip_ref.encode_image(sd, clip_ref.preprocess_u8(images))
@@ -333,3 +340,23 @@ def test_model_on_a_second_device(sd, golden_inputs):
     b = m1.encode_image(images.cuda(1), normalize=True).cpu()
     assert torch.equal(a, b)
     assert torch.equal(m0.encode_text(tokens.cuda(0)).cpu(), m1.encode_text(tokens.cuda(1)).cpu())
+
+
+def test_ln_fold_is_dropped_when_calibration_disagrees(sd, golden_inputs):
+    """A checkpoint whose residual stream carries a huge common-mode offset (ln_pre.bias + 1500 on
+    every channel) breaks E[x^2] - mean^2 in fp32: cb_clip_finalize must notice on its calibration
+    batch and keep LayerNorm as its own fp32 launch -- the result is then the unfolded model's, bit
+    for bit."""
+    import torch
+    from clipb200 import _native, clip
+    images, tokens, _ = golden_inputs
+    bad = {k: v.clone() for k, v in sd.items()}
+    bad["visual.ln_pre.bias"] = bad["visual.ln_pre.bias"] + 1500.0
+    auto = clip.CLIPB200(bad, device=0, max_image_batch=4, max_text_batch=4)
+    is_folded, cal_cos = auto.ln_fold_status()
+    assert not is_folded and -1.0 <= cal_cos < 0.9998, (is_folded, cal_cos)
+    with _native.tuning(ln_fold=0):
+        plain = clip.CLIPB200(bad, device=0, max_image_batch=4, max_text_batch=4)
+    a, b = auto.encode_image(images.cuda()), plain.encode_image(images.cuda())
+    assert torch.equal(a, b)
+    assert torch.equal(auto.encode_text(tokens.cuda()), plain.encode_text(tokens.cuda()))

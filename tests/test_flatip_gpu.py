@@ -138,8 +138,14 @@ def test_incremental_add_reconstruct_and_file_roundtrip(faiss, tmp_path):
     assert index.ntotal == 3000
     np.testing.assert_array_equal(index.reconstruct_n(0, 3000), xb)
     np.testing.assert_array_equal(index.reconstruct(1234), xb[1234])
-    ivf = faiss.IndexIVFFlat(index, 512, 100, faiss.METRIC_INNER_PRODUCT)
+    # the reference's construction (build-index.py:80-81,96,99): quantizer, IVF wrapper, train, add
+    quantizer = faiss.IndexFlatIP(512, storage="f32")
+    ivf = faiss.IndexIVFFlat(quantizer, 512, 100, faiss.METRIC_INNER_PRODUCT)
+    with pytest.raises(AssertionError):
+        ivf.add(xb)                                      # faiss refuses add() before train() too
     ivf.train(xb)
+    ivf.add(xb)
+    assert ivf.ntotal == 3000 and quantizer.ntotal == 0   # the quantizer is not the row store
     ivf.nprobe = 32
     path = str(tmp_path / "images.index")
     faiss.write_index(ivf, path)

@@ -47,18 +47,18 @@ def test_bias_epilogue(M, N, K):
 
 @pytest.mark.parametrize("ncta", ["1", "2"])
 @pytest.mark.parametrize("bn", ["64", "128", "192", "256"])
-def test_all_tile_widths(bn, ncta, monkeypatch):
+def test_all_tile_widths(bn, ncta):
     """Every (cluster size, N tile) instantiation, incl. an M tail inside a CTA pair."""
     import torch
     if bn == "64" and ncta == "2":
         pytest.skip("the 64-wide tile exists for single-CTA tiles only (M <= 128 row blocks)")
-    monkeypatch.setenv("CLIPB200_GEMM_BN", bn)
-    monkeypatch.setenv("CLIPB200_GEMM_NCTA", ncta)
+    from clipb200 import _native
     g = torch.Generator(device="cuda").manual_seed(int(bn))
     M, N, K = 1280 + 77, 768, 768
     A = (torch.randn((M, K), generator=g, device="cuda") * 0.5).half()
     W = (torch.randn((N, K), generator=g, device="cuda") * K ** -0.5).half()
-    out = _gemm(torch, A, W, bias=None)
+    with _native.tuning(gemm_bn=int(bn), gemm_ncta=int(ncta)):
+        out = _gemm(torch, A, W, bias=None)
     _close(torch, out, A.float() @ W.float().T)
 
 
