@@ -101,6 +101,9 @@ struct cb_clip {
     float *d_img_f32 = nullptr;     // fixed input slot of the fp32-image graphs (allocated on first use)
     // live GEMM timing (bench.py roofline)
     int timing = 0;                 // 0 off, 1 GEMM launches only, 2 every kernel class
+    unsigned long long *stamps = nullptr;   // device: (entry min, exit max) %globaltimer per timed GEMM launch
+    int stamp_n = 0;
+    static constexpr int kStamps = 8192;
     std::vector<cudaEvent_t> ev;
     std::vector<int> ev_cat;        // category of each event pair: 0 gemm, 1 attention, 2 layernorm, 3 other
     int ev_n = 0;
@@ -216,17 +219,16 @@ int bind_blocks(cb_clip *m, const char *prefix, int W, LayerW *lw) {
     return CB_OK;
 }
 
-int timed_gemm(cb_clip *m, const GemmArgs &g, cudaStream_t s) {
-    const bool t = m->timing && m->ev_n + 2 <= (int)m->ev.size();
-    if (t) CB_CUDA(cudaEventRecord(m->ev[m->ev_n], s));
+// GEMM launches are timed ON THE DEVICE (every CTA folds %globaltimer into a per-launch (min entry, max
+// exit) pair): the duration of a launch then excludes the host-side gaps that CUDA events bracket in
+int timed_gemm(cb_clip *m, const GemmArgs &g0, cudaStream_t s) {
+    if (!m->timing || m->stamp_n >= cb_clip::kStamps) return gemm_f16(g0, s);
+    GemmArgs g = g0;
+    g.stamp = m->stamps + 2 * (size_t)m->stamp_n;
     int rc = gemm_f16(g, s);
     if (rc) return rc;
-    if (t) {
-        CB_CUDA(cudaEventRecord(m->ev[m->ev_n + 1], s));
-        m->ev_cat[m->ev_n / 2] = 0;
-        m->ev_n += 2;
-        m->gemm_flops += 2.0 * g.M * g.N * g.K;
-    }
+    m->stamp_n++;
+    m->gemm_flops += 2.0 * g.M * g.N * g.K;
     return CB_OK;
 }
 
@@ -528,7 +530,7 @@ void cb_clip_free(cb_clip *m) {
     drop_graphs(m);
     for (auto &kv : m->params) cudaFree(kv.second.dev);
     free_ws(m->ws);
-    void *bufs[] = {m->d_img, m->d_ids, m->d_out, m->cls_pos, m->d_img_f32};
+    void *bufs[] = {m->d_img, m->d_ids, m->d_out, m->cls_pos, m->d_img_f32, m->stamps};
     for (void *p : bufs) cudaFree(p);
     for (cudaEvent_t ev : m->ev) cudaEventDestroy(ev);
     for (Lane &l : m->lanes) {
@@ -874,6 +876,15 @@ int cb_clip_timing(cb_clip *m, int enable) {
     m->timing = enable;
     m->ev_n = 0;
     m->gemm_flops = 0;
+    m->stamp_n = 0;
+    if (m->timing) {
+        if (!m->stamps) CB_CUDA(cudaMalloc(&m->stamps, (size_t)cb_clip::kStamps * 16));
+        // (min, max) pairs start at (all ones, 0); wait for launches that may still write the old ones
+        CB_CUDA(cudaDeviceSynchronize());
+        std::vector<unsigned long long> init((size_t)cb_clip::kStamps * 2);
+        for (size_t i = 0; i < init.size(); i += 2) { init[i] = ~0ull; init[i + 1] = 0ull; }
+        CB_CUDA(cudaMemcpy(m->stamps, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    }
     if (m->timing && m->ev.empty()) {
         m->ev.resize(8192);
         m->ev_cat.assign(4096, 0);
@@ -886,6 +897,13 @@ int cb_clip_timing_breakdown(cb_clip *m, double *ms_by_class4) {
     CB_REQUIRE(m && ms_by_class4, "cb_clip_timing_breakdown: null argument");
     DeviceGuard g(m->device);
     for (int i = 0; i < 4; i++) ms_by_class4[i] = 0;
+    CB_CUDA(cudaDeviceSynchronize());
+    if (m->stamp_n > 0) {
+        std::vector<unsigned long long> st((size_t)m->stamp_n * 2);
+        CB_CUDA(cudaMemcpy(st.data(), m->stamps, st.size() * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m->stamp_n; i++)
+            if (st[2 * i + 1] >= st[2 * i]) ms_by_class4[0] += (double)(st[2 * i + 1] - st[2 * i]) * 1e-6;
+    }
     for (int i = 0; i + 1 < m->ev_n; i += 2) {
         CB_CUDA(cudaEventSynchronize(m->ev[i + 1]));
         float ms = 0;
@@ -898,21 +916,22 @@ int cb_clip_timing_breakdown(cb_clip *m, double *ms_by_class4) {
 int cb_clip_timing_read(cb_clip *m, double *gemm_ms_total, double *gemm_flops, int *n_gemms) {
     CB_REQUIRE(m && gemm_ms_total && gemm_flops && n_gemms, "cb_clip_timing_read: null argument");
     DeviceGuard g(m->device);
+    CB_CUDA(cudaDeviceSynchronize());
     double tot = 0;
     int ng = 0;
-    for (int i = 0; i + 1 < m->ev_n; i += 2) {
-        if (m->ev_cat[i / 2] != 0) continue;
-        CB_CUDA(cudaEventSynchronize(m->ev[i + 1]));
-        float ms = 0;
-        CB_CUDA(cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]));
-        tot += ms;
-        ng++;
+    if (m->stamp_n > 0) {
+        std::vector<unsigned long long> st((size_t)m->stamp_n * 2);
+        CB_CUDA(cudaMemcpy(st.data(), m->stamps, st.size() * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m->stamp_n; i++)
+            if (st[2 * i + 1] >= st[2 * i]) { tot += (double)(st[2 * i + 1] - st[2 * i]) * 1e-6; ng++; }
     }
     *gemm_ms_total = tot;
     *gemm_flops = m->gemm_flops;
     *n_gemms = ng;
     m->ev_n = 0;
     m->gemm_flops = 0;
+    if (m->timing) return cb_clip_timing(m, m->timing);      // re-arm the stamp slots
+    m->stamp_n = 0;
     return CB_OK;
 }
 

@@ -39,6 +39,10 @@ struct GemmArgs {
     // values before the fp16 store) over each epilogue warp's column slice: stats_out[r][gemm_out_slices(M,N)][2].
     // One writer per slot: deterministic, nothing to zero.
     float *stats_out = nullptr;
+    // live timing (bench.py roofline): when set, every CTA folds %globaltimer into stamp[0] (min at
+    // kernel entry) and stamp[1] (max at exit), so the launch's duration is measured on the device
+    // without host-side event gaps.  Null in the product path.
+    unsigned long long *stamp = nullptr;
 };
 
 // returns a CB_* code; launches on `stream`

@@ -74,7 +74,7 @@ def test_queries_outside_fp16_range_are_still_exact():
     on-device selection instead of the filter."""
     from clipb200 import faiss
     xb = synth.unit_rows(20_000, seed=51)
-    xq = synth.unit_rows(8, seed=52)
+    xq = synth.unit_rows(24, seed=52)
     xq[3] *= 1e7
     index = faiss.IndexFlatIP(512, storage="f16", devices=[0])
     index.add(xb)
@@ -85,7 +85,7 @@ def test_queries_outside_fp16_range_are_still_exact():
     ok, _, msg = F.ids_match_with_tolerance(Dref[3:4], Iref[3:4], D[3:4], I[3:4], gap=1e-5 * 1e7)
     assert ok, msg
     np.testing.assert_allclose(D[3], Dref[3], rtol=1e-5)
-    keep = [i for i in range(8) if i != 3]
+    keep = [i for i in range(24) if i != 3]
     _check(D[keep], I[keep], Dref[keep], Iref[keep])
     assert _stats(index)[1] >= 1                         # the out-of-range query went through the exact path
 
