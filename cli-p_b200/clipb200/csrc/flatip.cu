@@ -699,10 +699,11 @@ static int search_core(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, 
         CB_LAUNCH_CHECK();
         return CB_OK;
     }
-    // The GEMM pass over 10M rows costs about the same whatever nq <= 128 is, the streaming scan 1.5 ms for
-    // one query, 1.9 ms for two, 2.9 ms for four and another pass per four after that.  Small shards keep a
-    // higher threshold: there both paths are bounded by their launch counts, not by the pass over the rows.
-    int64_t batch_min = ix->ntotal >= (1ll << 20) ? 3 : 16;
+    // The GEMM pass over 10M rows costs 1.7-1.9 ms whatever nq <= 128 is (HBM-bound, profiles/r02_search_probe.txt),
+    // the streaming scan 1.5 ms for one query, 1.9 ms for two, 2.6 ms for four and another pass per four after
+    // that.  Small shards keep a higher threshold: there both paths are bounded by their launch counts, not
+    // by the pass over the rows.
+    int64_t batch_min = ix->ntotal >= (1ll << 20) ? 2 : 16;
     if (tune(T_BATCH_MIN_NQ) > 0) batch_min = tune(T_BATCH_MIN_NQ);
     if (nq >= batch_min && ix->dtype == CB_F16 && k <= 1024 && ix->ntotal >= 8192) {
         if (!ix->bws) ix->bws = batch_ws_new();

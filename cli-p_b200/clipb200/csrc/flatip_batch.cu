@@ -13,8 +13,8 @@
 //            thr is the exact k-th best so far; margin = (2^-11 + 2^-16) |q| max|x| + 1e-6 bounds
 //            |<q - fp16(q), x>| plus the tensor core's accumulation error, so no row whose exact
 //            score beats thr is ever dropped.
-//   RE-SCORE between row ranges (they grow 1K, +4K, +16K ... so the expected survivors per range
-//            stay ~3k), one block per query computes the EXACT fp32 score of every new candidate
+//   RE-SCORE between row ranges (they grow 1K, +8K, +64K ... so the expected survivors per range
+//            stay ~7k), one block per query computes the EXACT fp32 score of every new candidate
 //            with the same summation order as the streaming scan (flatip.cuh): batch and scan
 //            answers are bit-identical, scores included.  It then sorts by (score desc, id asc),
 //            keeps k and raises thr.  Ranges ascend in id, so ties resolve exactly.
@@ -47,7 +47,6 @@ constexpr int KB = 512 / BK;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kCap = 8192;              // candidate slots per query between compactions
-constexpr int kCompactThreads = 512;
 constexpr int kMaxGroup = 1024;         // queries per pass over the shard (4 query blocks of 256)
 
 template <int NCTA>
@@ -284,26 +283,36 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t c) {
 // One block per query, after each row range [r0, r1): exact re-score of the new candidates (or an
 // exact re-read of the range if the list overflowed), sort, keep k, raise the threshold; on the
 // final range also write D / I (faiss padding) -- possibly into the root GPU's mailbox.
-__global__ void __launch_bounds__(kCompactThreads)
+// The usual list (k kept + a few hundred new) is handled in 16 KB of shared memory, so many query
+// blocks share an SM; longer lists and the rescue work in the query's global candidate buffer.
+constexpr int kSmemCap = 2048;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 batch_compact_kernel(uint64_t *__restrict__ cand, uint32_t *__restrict__ cnt, uint32_t *__restrict__ kept,
                      float *__restrict__ thr, float *__restrict__ thr_eff, const float *__restrict__ margin,
                      const uint32_t *__restrict__ bad, const uint4 *__restrict__ rows, const float *__restrict__ xq,
-                     int64_t k, int64_t r0, int64_t r1, int final_pass, const IdMap ids, const PeerOut po, float *__restrict__ D, int64_t *__restrict__ I,
-                     unsigned long long *rescued) {
-    extern __shared__ uint64_t s_c[];       // kCap entries
+                     int64_t k, int64_t r0, int64_t r1, int final_pass, const IdMap ids, const PeerOut po,
+                     float *__restrict__ D, int64_t *__restrict__ I, unsigned long long *rescued) {
+    __shared__ uint64_t s_c[kSmemCap];
     __shared__ uint32_t s_n;
     const int q = blockIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int nwarps = THREADS / 32;
     uint64_t *mine = cand + (size_t)q * kCap;
     const uint32_t c_raw = cnt[q], kp = kept[q];
     const bool rescue = c_raw > (uint32_t)kCap || bad[q] != 0;
     if (!final_pass && !rescue && c_raw == kp) return;  // nothing new in this range
     float qr[16];
     load_q_lane_f16(xq + (size_t)q * kD, lane, qr);
+    const bool in_smem = !rescue && c_raw <= (uint32_t)kSmemCap;
+    uint64_t *buf = in_smem ? s_c : mine;              // entries [0, kp) of `mine` are the kept (exact, sorted) ones
+    if (in_smem)
+        for (uint32_t i = threadIdx.x; i < kp; i += THREADS) s_c[i] = mine[i];
     uint32_t c;
     if (rescue) {
-        // RESCUE: survivors of this range were dropped.  Select exactly over [r0, r1) here.
-        for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) s_c[i] = mine[i];
+        // RESCUE: survivors of this range were dropped (or the query cannot be filtered in fp16).
+        // Select exactly over [r0, r1) here, in the global buffer.
         if (threadIdx.x == 0) { s_n = kp; atomicAdd(rescued, 1ull); }
         __syncthreads();
         float cur = kp == (uint32_t)k ? thr[q] : -INFINITY;
@@ -312,11 +321,11 @@ batch_compact_kernel(uint64_t *__restrict__ cand, uint32_t *__restrict__ cnt, ui
             if (s_n + kBatch > (uint32_t)kCap) {
                 // make room: sort, keep k, raise the running threshold (uniform branch: s_n is shared)
                 const uint32_t n_now = s_n, p2 = next_pow2(n_now);
-                for (uint32_t i = n_now + threadIdx.x; i < p2; i += blockDim.x) s_c[i] = 0ull;
+                for (uint32_t i = n_now + threadIdx.x; i < p2; i += THREADS) buf[i] = 0ull;
                 __syncthreads();
-                sort_desc(s_c, p2);
+                sort_desc(buf, p2);
                 const uint32_t keep = min(n_now, (uint32_t)k);
-                if (keep == (uint32_t)k) cur = key2f((uint32_t)(s_c[k - 1] >> 32));
+                if (keep == (uint32_t)k) cur = key2f((uint32_t)(buf[k - 1] >> 32));
                 __syncthreads();
                 if (threadIdx.x == 0) s_n = keep;
                 __syncthreads();
@@ -325,57 +334,67 @@ batch_compact_kernel(uint64_t *__restrict__ cand, uint32_t *__restrict__ cnt, ui
             for (int64_t r = b0 + wid; r < b1; r += nwarps) {
                 const float sc = exact_score_f16(rows + r * 64, qr, lane);
                 // rows ascend in id: an equal score later in the shard loses the tie
-                if (lane == 0 && sc > cur) s_c[atomicAdd(&s_n, 1u)] = make_comp(f2key(sc), (uint32_t)r);
+                if (lane == 0 && sc > cur) buf[atomicAdd(&s_n, 1u)] = make_comp(f2key(sc), (uint32_t)r);
             }
             __syncthreads();
         }
         c = s_n;
     } else {
         c = c_raw;
-        for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) s_c[i] = mine[i];
-        // exact fp32 score of every new candidate: one warp per row, two rows in flight
-        for (uint32_t i = kp + 2 * wid; i < c; i += 2 * nwarps) {
-            const uint32_t id0 = 0xffffffffu - (uint32_t)mine[i];
-            const bool two = i + 1 < c;
-            const uint32_t id1 = two ? 0xffffffffu - (uint32_t)mine[i + 1] : id0;
-            const uint4 *p0 = rows + (size_t)id0 * 64, *p1 = rows + (size_t)id1 * 64;
-            const uint4 a0 = ld_stream_v4(p0 + lane), a1 = ld_stream_v4(p0 + lane + 32);
-            const uint4 b0 = ld_stream_v4(p1 + lane), b1 = ld_stream_v4(p1 + lane + 32);
-            float s0 = 0.f, s1 = 0.f;
-            s0 += dot8_h(a0, &qr[0]); s0 += dot8_h(a1, &qr[8]);
-            s1 += dot8_h(b0, &qr[0]); s1 += dot8_h(b1, &qr[8]);
+        // exact fp32 score of every new candidate: one warp per row, four rows in flight per warp
+        for (uint32_t i = kp + 4 * wid; i < c; i += 4 * nwarps) {
+            uint32_t id[4];
+            uint4 v[4][2];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            for (int j = 0; j < 4; j++) {
+                id[j] = 0xffffffffu - (uint32_t)mine[min(i + j, c - 1)];
+                const uint4 *p = rows + (size_t)id[j] * 64;
+                v[j][0] = ld_stream_v4(p + lane);
+                v[j][1] = ld_stream_v4(p + lane + 32);
             }
-            if (lane == 0) {
-                s_c[i] = make_comp(f2key(s0 + 0.0f), id0);
-                if (two) s_c[i + 1] = make_comp(f2key(s1 + 0.0f), id1);
+            float sc[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float t = 0.f;
+                t += dot8_h(v[j][0], &qr[0]);
+                t += dot8_h(v[j][1], &qr[8]);
+                sc[j] = t;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 4; j++) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+            if (lane < 4 && i + lane < c) {
+                const float mys = lane == 0 ? sc[0] : lane == 1 ? sc[1] : lane == 2 ? sc[2] : sc[3];
+                const uint32_t myid = lane == 0 ? id[0] : lane == 1 ? id[1] : lane == 2 ? id[2] : id[3];
+                buf[i + lane] = make_comp(f2key(mys + 0.0f), myid);
             }
         }
         __syncthreads();
     }
-    const uint32_t p2 = next_pow2(c);
-    for (uint32_t i = c + threadIdx.x; i < p2; i += blockDim.x) s_c[i] = 0ull;
-    __syncthreads();
-    sort_desc(s_c, p2);
     const uint32_t keep = min(c, (uint32_t)k);
-    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = s_c[i];
+    if (c > kp || final_pass) {
+        const uint32_t p2 = next_pow2(c);
+        for (uint32_t i = c + threadIdx.x; i < p2; i += THREADS) buf[i] = 0ull;
+        __syncthreads();
+        sort_desc(buf, p2);
+        if (in_smem)
+            for (uint32_t i = threadIdx.x; i < keep; i += THREADS) mine[i] = s_c[i];
+    }
     if (threadIdx.x == 0) {
         cnt[q] = keep;
         kept[q] = keep;
         if (keep == (uint32_t)k) {
-            const float t = key2f((uint32_t)(s_c[k - 1] >> 32));
+            const float t = key2f((uint32_t)(buf[k - 1] >> 32));
             thr[q] = t;
             thr_eff[q] = t - margin[q];
         }
     }
     if (final_pass) {
         peer_wait_slot(po);
-        for (int64_t j = threadIdx.x; j < k; j += blockDim.x) {
+        for (int64_t j = threadIdx.x; j < k; j += THREADS) {
             if (j < keep) {
-                const uint64_t e = s_c[j];
+                const uint64_t e = buf[j];
                 D[(size_t)q * k + j] = key2f((uint32_t)(e >> 32));
                 I[(size_t)q * k + j] = map_id(ids, 0xffffffffu - (uint32_t)e);
             } else {
@@ -506,8 +525,8 @@ static int search_group(BatchWs *w, const void *rows_f16, int64_t n, int sms, in
     int rc;
     if ((rc = make_map(&tmQ, w->qh, (uint64_t)nq_pad, kD, QM))) return rc;
     if ((rc = make_map(&tmX, rows_f16, (uint64_t)n, kD, RN / ncta))) return rc;
-    // row ranges grow geometrically so the expected survivors per range stay ~3k (k m / n_seen); few queries
-    // can afford longer ranges (fewer launches on the HBM-bound small-nq pass)
+    // row ranges grow geometrically (x8) so the expected survivors per range stay ~7k (k m / n_seen); few
+    // queries can afford longer ranges (fewer launches on the HBM-bound small-nq pass)
     const int64_t span_max = nq <= QM ? (16ll << 20) : (4ll << 20);
     int64_t r0 = 0, span = 1024;
     while (r0 < n) {
@@ -516,12 +535,19 @@ static int search_group(BatchWs *w, const void *rows_f16, int64_t n, int sms, in
                        : launch_range<1>(tmQ, tmX, r0, r1, nq, q_blocks, sms, w, s);
         if (rc) return rc;
         const int final_pass = r1 >= n ? 1 : 0;
-        batch_compact_kernel<<<(unsigned)nq, kCompactThreads, kCap * 8, s>>>(
-            w->cand, w->cnt, w->kept, w->thr, w->thr_eff, w->margin, w->bad, (const uint4 *)rows_f16, q_dev, k, r0, r1,
-            final_pass, ids, po, D_dev, I_dev, w->rescued);
+        // few queries: one wave of big blocks (the re-score is a chain of dependent row gathers per warp);
+        // many queries: small blocks, eight per SM
+        if (nq <= 2 * sms)
+            batch_compact_kernel<512><<<(unsigned)nq, 512, 0, s>>>(
+                w->cand, w->cnt, w->kept, w->thr, w->thr_eff, w->margin, w->bad, (const uint4 *)rows_f16, q_dev, k, r0,
+                r1, final_pass, ids, po, D_dev, I_dev, w->rescued);
+        else
+            batch_compact_kernel<256><<<(unsigned)nq, 256, 0, s>>>(
+                w->cand, w->cnt, w->kept, w->thr, w->thr_eff, w->margin, w->bad, (const uint4 *)rows_f16, q_dev, k, r0,
+                r1, final_pass, ids, po, D_dev, I_dev, w->rescued);
         CB_LAUNCH_CHECK();
         r0 = r1;
-        span = std::min<int64_t>(span * 4, span_max);
+        span = std::min<int64_t>(span * 8, span_max);
     }
     return CB_OK;
 }
@@ -537,8 +563,6 @@ int flatip_search_batch(BatchWs *w, const void *rows_f16, int64_t n, int device,
         attr_err = cudaFuncSetAttribute(flatip_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<1>::SMEM_BYTES);
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(flatip_batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<2>::SMEM_BYTES);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(batch_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8);
     });
     CB_CUDA(attr_err);
     int sms = kNumSMs;

@@ -44,7 +44,7 @@ int cb_device_count(int *n);
 /* Process-wide tuning knobs (tests, profiling).  Each knob is read ONCE from the environment variable
  * CLIPB200_<NAME IN CAPITALS> when the library is loaded; launch paths never call getenv.  -1 = default.
  *   gemm_bn, gemm_ncta, gemm_stages, gemm_raster   tcgen05 GEMM tile shape / ring depth / tile order
- *   batch_min_nq       smallest query batch served by the tensor-core search (default 3 on shards of
+ *   batch_min_nq       smallest query batch served by the tensor-core search (default 2 on shards of
  *                      >= 1M rows, 16 below)
  *   no_graph           1: small encode_* calls are never replayed as CUDA graphs
  *   ln_blocks_per_sm   LayerNorm grid size
