@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclipb200.so")
+# CLIPB200_LIB: load another build of the same library (profiles/ uses the -DCLIPB200_EXPERIMENTS variant)
+LIB_PATH = os.environ.get("CLIPB200_LIB") or os.path.join(_HERE, "libclipb200.so")
 
 CB_OK, CB_ERR_INVALID, CB_ERR_CUDA, CB_ERR_NOGPU, CB_ERR_OOM, CB_ERR_IO = range(6)
 CB_F32, CB_F16 = 0, 1
@@ -101,6 +102,7 @@ SIGNATURES = {
     "cb_flatip_batch_stats": (_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "cb_flatip_timing": (_int, [_p, _int]),
     "cb_flatip_timing_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(_int)]),
+    "cb_flatip_phase_times": (_int, [_p, C.POINTER(C.c_double)]),
 }
 
 

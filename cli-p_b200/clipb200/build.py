@@ -45,20 +45,32 @@ def nvcc_path() -> str:
     return "nvcc"
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """experiments=True builds libclipb200_exp.so with -DCLIPB200_EXPERIMENTS: the same library plus the
+    result-corrupting perf probes (gemm_debug / skip knobs) that profiles/gemm_decompose.py uses.  Load
+    it with CLIPB200_LIB=<path>; the product library never contains them."""
+    if experiments:
+        return _build_variant(os.path.join(HERE, "libclipb200_exp.so"), os.path.join(HERE, "build_exp"),
+                              ["-DCLIPB200_EXPERIMENTS"], verbose)
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == dig:
                 return LIB
+    _build_variant(LIB, os.path.join(HERE, "build"), [], verbose)
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+def _build_variant(lib: str, objdir: str, extra, verbose: bool) -> str:
     objs = []
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -74,15 +86,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"nvcc failed on {src}\n")
     if failed:
         raise RuntimeError("libclipb200 build failed")
-    link = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    link = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("libclipb200 link failed")
-    with open(STAMP, "w") as fh:
-        fh.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

@@ -3,21 +3,17 @@
 // Replaces faiss.IndexFlatIP.search as called at /root/reference/query-index.py:111
 // (index built at /root/reference/build-index.py:80-81,99,107).
 //
-// Small-nq path (this file): HBM-bound.  One pass over the shard with coalesced
-// 128-bit streaming loads, fp32 FMA on CUDA cores (free when HBM-bound), a
-// transposed warp-shuffle reduction, scores written once (4 B/row = 0.4 % of the
-// 1024 B/row read) and an exact radix select over the fp32 scores:
-//
-//   K1 scan      : scores[q][i] = <q, x_i>; fused histogram of the top 11 key bits
-//   K2 refine x2 : histogram of the next 11 / last 10 key bits inside the selected bin
-//                  (reads only the 4 B/row scores, L2-resident; skipped once the bin is
-//                  taken whole)
-//   K3 collect   : gather the k winners, order ties by id, bitonic sort, write D/I
-//
-// The "find the bin that holds the k-th key" step of every kernel runs in its last
-// block to retire (threadfence + atomic ticket), so a search is 4 launches, no host
-// round trip, any k from 1 to ntotal.  Order is the total order (-score, id): results
-// do not depend on the launch geometry, so 1-GPU and sharded results are identical.
+// Small-nq path (this file): HBM-bound.  ONE cooperative launch per search
+// (flatip_search_kernel): a pass over the shard with coalesced 128-bit streaming loads,
+// fp32 FMA on CUDA cores (free when HBM-bound), a transposed warp-shuffle reduction,
+// scores written once (4 B/row = 0.4 % of the 1024 B/row read) with a fused histogram
+// over 2048 linear score bins; a grid barrier; then the bin holding the k-th score is
+// known, the few rows at or above it are gathered from the (L2-resident) scores, and the
+// last block to retire sorts them, orders ties by id and writes D / I.  Degenerate score
+// distributions (ties, constant rows) and very large k fall back, inside the same launch,
+// to an exact radix select over the 32 key bits.  No host round trip, any k from 1 to
+// ntotal.  Order is the total order (-score, id): results do not depend on the launch
+// geometry, so 1-GPU and sharded results are identical.
 #include "common.cuh"
 #include "flatip.cuh"
 
@@ -38,27 +34,29 @@ int flatip_search_batch(BatchWs *w, const void *rows_f16, int64_t n, int device,
                         const float *max_norm2, cudaStream_t s);
 int batch_ws_stats(BatchWs *w, int64_t *rescued, cudaStream_t s);
 
-constexpr int kBins0 = 2048;           // 11 + 11 + 10 bit digits
+constexpr int kBins0 = 2048;           // bins per histogram level
 constexpr int kMaxNQ = 4;              // queries sharing one pass over the shard (register budget)
 constexpr int kSortSmem = 4096;        // composite keys sorted in shared memory
 constexpr int kScanThreads = 256;
 constexpr int kPostThreads = 256;
 
 struct SelState {
-    uint32_t prefix;     // selected key prefix, right aligned, `bits` wide
+    uint32_t prefix;     // radix levels: selected key prefix, right aligned, `bits` wide
     uint32_t bits;       // prefix bits fixed so far: 0, 11, 22, 32
-    uint32_t k_rem;      // winners still to take from inside the prefix bin
-    uint32_t cnt_bin;    // elements inside the prefix bin
+    uint32_t k_rem;      // winners still to take from inside the selected bin
+    uint32_t cnt_bin;    // elements inside the selected bin
     uint32_t done;       // 1: cnt_bin == k_rem -> whole bin wins, stop refining
     uint32_t n_cand;     // collect cursor
-    uint32_t ticket[4];  // block-retire counters, one per kernel
-    uint32_t pad[6];
+    uint32_t ticket;     // block-retire counter of the collect phase
+    uint32_t bar;        // grid barrier counter (ws[0] only)
+    uint32_t pad[8];
 };
 static_assert(sizeof(SelState) == 64, "SelState layout");
 
-// workspace per query: 3 histograms + state
+// workspace per query: level 0 = linear score bins, levels 1..3 = radix digits (11 + 11 + 10 bits) of
+// the float key inside the level-0 bin; + state.  All zero between searches.
 struct QueryWs {
-    uint32_t hist[3][kBins0];
+    uint32_t hist[4][kBins0];
     SelState st;
 };
 
@@ -78,6 +76,7 @@ __device__ void find_bin(const uint32_t *hist, int nbins, int digit_bits, SelSta
     }
     const uint32_t excl = incl - s;
     const uint32_t k_rem = st->k_rem;
+    __syncwarp();
     if (excl < k_rem && incl >= k_rem) {
         uint32_t acc = excl;
         for (int i = 0; i < per; i++) {
@@ -107,6 +106,23 @@ __device__ bool last_block(uint32_t *ticket, uint32_t nblocks) {
     return s_last;
 }
 
+// Grid-wide barrier for a kernel launched COOPERATIVELY (every block resident).  `ctr` counts
+// arrivals since the workspace was last zeroed; `epoch` = barriers passed so far in this launch.
+__device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t &epoch) {
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        const uint32_t want = epoch * gridDim.x;
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < want);
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------
 // transposed reduction: R per-lane partial sums -> lane l holds the full sum of row
 // (l >> (5 - log2 R)); 1 + R shuffles instead of 5 R.
@@ -129,123 +145,21 @@ __device__ __forceinline__ float reduce_rows(float (&v)[R], int lane) {
     return t;
 }
 
-// K1: one pass over the shard.  Row = 512 elements: fp16 -> 64 x 16 B chunks (lane
-// takes chunks lane, lane+32), fp32 -> 128 chunks (lane, +32, +64, +96); either way a
-// lane owns 16 elements of every row and keeps the matching 16 query values per query
-// in registers.  R rows in flight per warp iteration (16 x 128-bit loads per lane).
-template <int NQ, bool F16>
-__global__ void __launch_bounds__(kScanThreads)
-flatip_scan_kernel(const uint4 *__restrict__ xb, int64_t n, const float *__restrict__ xq,
-                   int nq_valid, float *__restrict__ scores, int64_t stride, QueryWs *ws,
-                   uint32_t k_eff) {
-    constexpr int R = F16 ? 8 : 4;          // rows per warp iteration
-    constexpr int CH = F16 ? 2 : 4;         // chunks per lane per row
-    constexpr int EPC = F16 ? 8 : 4;        // elements per chunk
-    constexpr int ROW_V4 = F16 ? 64 : 128;  // uint4 per row
-    extern __shared__ uint32_t s_hist[];    // [NQ][kBins0]
-
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < NQ * kBins0; i += blockDim.x) s_hist[i] = 0;
-
-    float qreg[NQ][CH * EPC];
+// selection state as other blocks left it (written between grid barriers): read through L2
+__device__ __forceinline__ SelState load_state(const SelState *p) {
+    SelState st;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p);
+    uint4 *dst = reinterpret_cast<uint4 *>(&st);
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        const float *qp = xq + (size_t)min(q, nq_valid - 1) * kD;
-#pragma unroll
-        for (int c = 0; c < CH; c++)
-#pragma unroll
-            for (int e = 0; e < EPC; e++) qreg[q][c * EPC + e] = qp[(lane + 32 * c) * EPC + e];
-    }
-    __syncthreads();
-
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t groups = (n + R - 1) / R;
-    constexpr int SH = F16 ? 2 : 3;         // lanes sharing a row after reduce = 1 << SH
-    const int my_row = lane >> SH;
-
-    for (int64_t g = gw; g < groups; g += warps) {
-        const int64_t row0 = g * R;
-        uint4 v[R][CH];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int64_t row = min(row0 + r, n - 1);
-            const uint4 *p = xb + row * ROW_V4 + lane;
-#pragma unroll
-            for (int c = 0; c < CH; c++) v[r][c] = ld_stream_v4(p + 32 * c);
-        }
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            float acc[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                float s = 0.f;
-#pragma unroll
-                for (int c = 0; c < CH; c++) {
-                    if (F16) s += dot8_h(v[r][c], &qreg[q][c * EPC]);
-                    else     s += dot4_f(v[r][c], &qreg[q][c * EPC]);
-                }
-                acc[r] = s;
-            }
-            float tot = reduce_rows<R>(acc, lane);
-            const int64_t row = row0 + my_row;
-            if ((lane & ((1 << SH) - 1)) == 0 && row < n && q < nq_valid) {
-                tot += 0.0f;
-                scores[(size_t)q * stride + row] = tot;
-                atomicAdd(&s_hist[q * kBins0 + (f2key(tot) >> 21)], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NQ * kBins0; i += blockDim.x) {
-        uint32_t c = s_hist[i];
-        int q = i / kBins0;
-        if (c && q < nq_valid) atomicAdd(&ws[q].hist[0][i - q * kBins0], c);
-    }
-    if (last_block(&ws[0].st.ticket[0], gridDim.x)) {
-        const int w = threadIdx.x >> 5;
-        for (int q = w; q < nq_valid; q += (blockDim.x >> 5)) {
-            if (lane == 0) ws[q].st.k_rem = k_eff;
-            __syncwarp();
-            find_bin(ws[q].hist[0], kBins0, 11, &ws[q].st);
-        }
-    }
+    for (int i = 0; i < 4; i++) dst[i] = __ldcg(src + i);
+    return st;
 }
 
-// K2: refine the selected bin by the next digit.  grid = (blocks, nq).
-__global__ void __launch_bounds__(kPostThreads)
-flatip_refine_kernel(const float *__restrict__ scores, int64_t n, int64_t stride, QueryWs *ws,
-                     int pass /*1 or 2*/) {
-    QueryWs *w = ws + blockIdx.y;
-    const SelState st = w->st;
-    if (st.done) return;                       // uniform over the whole grid
-    const int digit_bits = pass == 1 ? 11 : 10;
-    const int shift_prev = 32 - (int)st.bits;  // st.bits is 11 or 22 here
-    const int shift = shift_prev - digit_bits;
-    const uint32_t mask = (1u << digit_bits) - 1;
-    __shared__ uint32_t s_h[kBins0];
-    for (int i = threadIdx.x; i < kBins0; i += blockDim.x) s_h[i] = 0;
-    __syncthreads();
-    const float4 *s4 = reinterpret_cast<const float4 *>(scores + (size_t)blockIdx.y * stride);
-    const int64_t n4 = (n + 3) / 4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        float4 f = __ldcg(s4 + i);
-        const float e[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (i * 4 + j < n) {
-                uint32_t key = f2key(e[j]);
-                if ((key >> shift_prev) == st.prefix) atomicAdd(&s_h[(key >> shift) & mask], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (1 << digit_bits); i += blockDim.x)
-        if (s_h[i]) atomicAdd(&w->hist[pass][i], s_h[i]);
-    if (last_block(&w->st.ticket[pass], gridDim.x)) {
-        if (threadIdx.x < 32) find_bin(w->hist[pass], 1 << digit_bits, digit_bits, &w->st);
-    }
+// level-0 bin of a score: linear over [-B, B] with B >= |q| max|x| (so every score is in range),
+// 2048 bins.  Monotone non-decreasing in s, hence a higher bin always means a higher score.
+__device__ __forceinline__ int lin_bin(float s, float scale) {
+    const int b = (int)floorf(fmaf(s, scale, 1024.f));
+    return min(kBins0 - 1, max(0, b));
 }
 
 // descending bitonic sort of n_pow2 composite keys by the whole block
@@ -279,93 +193,284 @@ __device__ void emit_sorted(const uint64_t *a, uint32_t count, int64_t k, const 
     }
 }
 
-// K3: gather winners; the last block orders exact ties by id, sorts and writes D/I (possibly
-// straight into the root GPU's mailbox, see PeerOut), then clears the query's workspace so the
-// next search needs no memset.
-__global__ void __launch_bounds__(kPostThreads)
-flatip_collect_kernel(const float *__restrict__ scores_all, int64_t n, int64_t stride, QueryWs *ws,
-                      uint64_t *cand_all, uint32_t cand_cap, int64_t k, const IdMap ids, const PeerOut po,
-                      float *D_all, int64_t *I_all) {
-    QueryWs *w = ws + blockIdx.y;
-    const SelState st = w->st;
-    const float *scores = scores_all + (size_t)blockIdx.y * stride;
-    uint64_t *cand = cand_all + (size_t)blockIdx.y * cand_cap;
-    const int sh = 32 - (int)st.bits;   // 0 when all 32 bits are fixed
-    const float4 *s4 = reinterpret_cast<const float4 *>(scores);
-    const int64_t n4 = (n + 3) / 4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        float4 f = __ldcg(s4 + i);
-        const float e[4] = {f.x, f.y, f.z, f.w};
+// The whole small-nq search in ONE cooperative launch.
+//
+// Phase 1 (HBM-bound, >= 96 % of the time): one pass over the shard.  Row = 512 elements: fp16 ->
+//   64 x 16 B chunks (lane takes chunks lane, lane+32), fp32 -> 128 chunks (lane, +32, +64, +96);
+//   a lane owns 16 elements of every row and keeps the matching 16 query values per query in
+//   registers.  R rows in flight per warp iteration (16 x 128-bit loads per lane), fp32 FMA, the
+//   transposed shuffle reduction, scores written once (4 B/row), and a histogram of the scores over
+//   2048 LINEAR bins spanning [-|q| max|x|, +|q| max|x|].
+// -- grid barrier --
+// Phase 2: every block finds the bin b0 that holds the k-th best score.  With 2048 linear bins the
+//   rows in bins >= b0 are usually only a little more than k ("short list"): phase 3 takes them all.
+//   Otherwise (k too large for shared memory, or scores piled into one bin: ties, constant rows) an
+//   exact radix select over the 32 key bits runs inside bin b0 (3 more histogram levels, two grid
+//   barriers each) -- same result, more passes over the 4 B/row scores.
+// Phase 3: every block gathers its share of the winners as 64-bit (key, ~id) composites; the last
+//   block to retire orders exact ties by id, sorts, writes D / I (possibly straight into the root
+//   GPU's mailbox, see PeerOut) and zeroes the workspace for the next search.
+// Order is the total order (-score, id): the result does not depend on the launch geometry, so
+// 1-GPU and sharded answers are identical.
+template <int NQ, bool F16>
+__global__ void __launch_bounds__(kScanThreads)
+flatip_search_kernel(const uint4 *__restrict__ xb, int64_t n, const float *__restrict__ xq,
+                     int nq_valid, float *__restrict__ scores, int64_t stride, QueryWs *ws,
+                     uint32_t k_eff, int64_t k, uint64_t *cand_all, uint32_t cand_cap,
+                     const float *__restrict__ max_norm2, const IdMap ids, const PeerOut po,
+                     float *D_all, int64_t *I_all, unsigned long long *phase_t) {
+    constexpr int R = F16 ? 8 : 4;          // rows per warp iteration
+    // optional phase stamps (cb_flatip_timing): block 0 at entry / after the scan's barrier / before the
+    // gather; the last block of the last query at exit
+    auto stamp = [&](int i) {
+        if (phase_t != nullptr && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            phase_t[i] = t;
+        }
+    };
+    if (blockIdx.x == 0) stamp(0);
+    constexpr int CH = F16 ? 2 : 4;         // chunks per lane per row
+    constexpr int EPC = F16 ? 8 : 4;        // elements per chunk
+    constexpr int ROW_V4 = F16 ? 64 : 128;  // uint4 per row
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // phase 1: [NQ][kBins0] histograms; later: scratch / sort
+    __shared__ SelState s_l0[NQ];           // this block's copy of the level-0 decision per query
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_filled;
+    __shared__ float s_scale[NQ];
+    uint32_t *s_hist = s_dyn;
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NQ * kBins0; i += blockDim.x) s_hist[i] = 0;
+
+    float qreg[NQ][CH * EPC];
+    float qscale[NQ];
+    {
+        const float mx = sqrtf(__ldg(max_norm2));
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int64_t row = i * 4 + j;
-            if (row < n) {
-                uint32_t key = f2key(e[j]);
-                uint32_t kp = sh ? (key >> sh) : key;
-                if (kp > st.prefix || (kp == st.prefix && st.done)) {
+        for (int q = 0; q < NQ; q++) {
+            const float *qp = xq + (size_t)min(q, nq_valid - 1) * kD;
+            float n2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; c++)
+#pragma unroll
+                for (int e = 0; e < EPC; e++) {
+                    const float v = qp[(lane + 32 * c) * EPC + e];
+                    qreg[q][c * EPC + e] = v;
+                    n2 = fmaf(v, v, n2);
+                }
+            n2 = warp_sum(n2);
+            const float bound = sqrtf(n2) * mx * 1.001f + 1e-30f;     // |<q, x>| <= |q| |x| (+ rounding slack)
+            qscale[q] = 1024.f / bound;                                // inf / 0 for degenerate input: one bin, radix path
+            if (threadIdx.x == 0) s_scale[q] = qscale[q];
+        }
+    }
+    __syncthreads();
+
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    const int64_t groups = (n + R - 1) / R;
+    constexpr int SH = F16 ? 2 : 3;         // lanes sharing a row after reduce = 1 << SH
+    const int my_row = lane >> SH;
+
+    for (int64_t g = gw; g < groups; g += warps) {
+        const int64_t row0 = g * R;
+        uint4 v[R][CH];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int64_t row = min(row0 + r, n - 1);
+            const uint4 *p = xb + row * ROW_V4 + lane;
+#pragma unroll
+            for (int c = 0; c < CH; c++) v[r][c] = ld_stream_v4(p + 32 * c);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            float acc[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    if (F16) s += dot8_h(v[r][c], &qreg[q][c * EPC]);
+                    else     s += dot4_f(v[r][c], &qreg[q][c * EPC]);
+                }
+                acc[r] = s;
+            }
+            float tot = reduce_rows<R>(acc, lane);
+            const int64_t row = row0 + my_row;
+            if ((lane & ((1 << SH) - 1)) == 0 && row < n && q < nq_valid) {
+                tot += 0.0f;
+                scores[(size_t)q * stride + row] = tot;
+                atomicAdd(&s_hist[q * kBins0 + lin_bin(tot, qscale[q])], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NQ * kBins0; i += blockDim.x) {
+        uint32_t c = s_hist[i];
+        int q = i / kBins0;
+        if (c && q < nq_valid) atomicAdd(&ws[q].hist[0][i - q * kBins0], c);
+    }
+    uint32_t epoch = 0;
+    uint32_t *bar = &ws[0].st.bar;
+    grid_barrier(bar, epoch);
+    if (blockIdx.x == 0) stamp(1);
+
+    // ---- phase 2: level-0 decision, computed by every block for itself (2048 counters per query)
+    if (wid < nq_valid && wid < NQ) {
+        SelState *l0 = &s_l0[wid];
+        if (lane == 0) { l0->prefix = 0; l0->bits = 0; l0->k_rem = k_eff; l0->cnt_bin = 0; l0->done = 0; }
+        __syncwarp();
+        find_bin(ws[wid].hist[0], kBins0, 11, l0);
+    }
+    __syncthreads();
+    const uint32_t short_cap = min(cand_cap, (uint32_t)kSortSmem);
+    bool need_radix = false;                 // uniform over the grid: derived from the global histograms
+    for (int q = 0; q < nq_valid; q++)
+        need_radix |= (k_eff - s_l0[q].k_rem + s_l0[q].cnt_bin) > short_cap;
+
+    const int64_t n4 = (n + 3) / 4;
+    if (need_radix) {
+        // exact radix select over the key bits of the rows inside bin b0 (per query that needs it)
+        for (int pass = 1; pass <= 3; pass++) {
+            const int digit_bits = pass == 3 ? 10 : 11;
+            bool any = false;
+            for (int q = 0; q < nq_valid; q++) {
+                const SelState l0 = s_l0[q];
+                if ((k_eff - l0.k_rem + l0.cnt_bin) <= short_cap) continue;
+                const SelState st = load_state(&ws[q].st);         // radix state (block 0 writes it between barriers)
+                if (pass > 1 && st.done) continue;
+                any = true;
+                const int shift_prev = 32 - (int)st.bits;          // 32, 21, 10
+                const int shift = shift_prev - digit_bits;
+                const uint32_t mask = (1u << digit_bits) - 1;
+                for (int i = threadIdx.x; i < kBins0; i += blockDim.x) s_dyn[i] = 0;
+                __syncthreads();
+                const float4 *s4 = reinterpret_cast<const float4 *>(scores + (size_t)q * stride);
+                for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+                    float4 f = __ldcg(s4 + i);
+                    const float e[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (i * 4 + j < n && lin_bin(e[j], s_scale[q]) == (int)l0.prefix) {
+                            const uint32_t key = f2key(e[j]);
+                            if (pass == 1 || (key >> shift_prev) == st.prefix) atomicAdd(&s_dyn[(key >> shift) & mask], 1u);
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < (1 << digit_bits); i += blockDim.x)
+                    if (s_dyn[i]) atomicAdd(&ws[q].hist[pass][i], s_dyn[i]);
+                __syncthreads();
+            }
+            if (!any) break;                                       // uniform
+            grid_barrier(bar, epoch);
+            if (blockIdx.x == 0 && wid < nq_valid && wid < NQ) {
+                const SelState l0 = s_l0[wid];
+                if ((k_eff - l0.k_rem + l0.cnt_bin) > short_cap && !(pass > 1 && load_state(&ws[wid].st).done)) {
+                    if (pass == 1 && lane == 0) ws[wid].st.k_rem = l0.k_rem;
+                    __syncwarp();
+                    __threadfence();
+                    find_bin(ws[wid].hist[pass], 1 << digit_bits, digit_bits, &ws[wid].st);
+                }
+            }
+            grid_barrier(bar, epoch);
+        }
+    }
+
+    // ---- phase 3: gather the winners; the last block per query sorts and writes
+    if (blockIdx.x == 0) stamp(2);
+    uint64_t *s_sort = reinterpret_cast<uint64_t *>(s_dyn);
+    for (int q = 0; q < nq_valid; q++) {
+        QueryWs *w = ws + q;
+        const SelState l0 = s_l0[q];
+        const bool is_short = (k_eff - l0.k_rem + l0.cnt_bin) <= short_cap;
+        const SelState st = load_state(&w->st);
+        const float *sc = scores + (size_t)q * stride;
+        uint64_t *cand = cand_all + (size_t)q * cand_cap;
+        const int sh = 32 - (int)st.bits;   // 0 when all 32 bits are fixed
+        const float4 *s4 = reinterpret_cast<const float4 *>(sc);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+            float4 f = __ldcg(s4 + i);
+            const float e[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t row = i * 4 + j;
+                if (row >= n) continue;
+                const int b = lin_bin(e[j], s_scale[q]);
+                bool take = b > (int)l0.prefix;
+                uint32_t key = 0;
+                if (b >= (int)l0.prefix) key = f2key(e[j]);
+                if (b == (int)l0.prefix) {
+                    if (is_short) take = true;
+                    else {
+                        const uint32_t kp = sh ? (sh < 32 ? (key >> sh) : 0u) : key;
+                        take = kp > st.prefix || (kp == st.prefix && st.done);
+                    }
+                }
+                if (take) {
                     uint32_t pos = atomicAdd(&w->st.n_cand, 1u);
                     if (pos < cand_cap) cand[pos] = make_comp(key, (uint32_t)row);
                 }
             }
         }
-    }
-    if (!last_block(&w->st.ticket[3], gridDim.x)) return;
+        if (!last_block(&w->st.ticket, gridDim.x)) continue;
 
-    __shared__ uint64_t s_sort[kSortSmem];
-    __shared__ uint32_t s_warp[kPostThreads / 32];
-    __shared__ uint32_t s_filled;
-    uint32_t count = *((volatile uint32_t *)&w->st.n_cand);
-    if (!st.done) {
-        // exact ties at the k-th key (all 32 bits fixed, more equal keys than slots):
-        // take the k_rem lowest ids in row order.
-        if (threadIdx.x == 0) s_filled = 0;
-        __syncthreads();
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int64_t base = 0; base < n; base += blockDim.x) {
-            const int64_t row = base + threadIdx.x;
-            bool hit = row < n && f2key(__ldcg(scores + row)) == st.prefix;
-            uint32_t bal = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) s_warp[wid] = __popc(bal);
+        uint32_t count = *((volatile uint32_t *)&w->st.n_cand);
+        if (!is_short && !st.done) {
+            // exact ties at the k-th key (all 32 bits fixed, more equal keys than slots):
+            // take the k_rem lowest ids in row order.
+            if (threadIdx.x == 0) s_filled = 0;
             __syncthreads();
-            uint32_t before = s_filled;
-            for (int x = 0; x < wid; x++) before += s_warp[x];
-            uint32_t rank = before + __popc(bal & ((1u << lane) - 1));
-            if (hit && rank < st.k_rem) cand[count + rank] = make_comp(st.prefix, (uint32_t)row);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t tot = 0;
-                for (int x = 0; x < (int)(blockDim.x >> 5); x++) tot += s_warp[x];
-                s_filled += tot;
+            for (int64_t base = 0; base < n; base += blockDim.x) {
+                const int64_t row = base + threadIdx.x;
+                bool hit = row < n && f2key(__ldcg(sc + row)) == st.prefix;
+                uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_warp[wid] = __popc(bal);
+                __syncthreads();
+                uint32_t before = s_filled;
+                for (int x = 0; x < wid; x++) before += s_warp[x];
+                uint32_t rank = before + __popc(bal & ((1u << lane) - 1));
+                if (hit && rank < st.k_rem) cand[count + rank] = make_comp(st.prefix, (uint32_t)row);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    uint32_t tot = 0;
+                    for (int x = 0; x < (int)(blockDim.x >> 5); x++) tot += s_warp[x];
+                    s_filled += tot;
+                }
+                __syncthreads();
+                if (s_filled >= st.k_rem) break;
             }
+            count += st.k_rem;
+            __threadfence_block();
             __syncthreads();
-            if (s_filled >= st.k_rem) break;
         }
-        count += st.k_rem;
-        __threadfence_block();
+        uint32_t p2 = 1;
+        while (p2 < count) p2 <<= 1;
+        float *D = D_all + (size_t)q * k;
+        int64_t *I = I_all + (size_t)q * k;
+        if (p2 <= (uint32_t)kSortSmem) {
+            for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) s_sort[i] = i < count ? __ldcg(cand + i) : 0ull;
+            __syncthreads();
+            bitonic_desc(s_sort, p2);
+            peer_wait_slot(po);
+            emit_sorted(s_sort, min(count, k_eff), k, ids, D, I);
+        } else {
+            for (uint32_t i = count + threadIdx.x; i < p2; i += blockDim.x) cand[i] = 0ull;
+            __syncthreads();
+            bitonic_desc(cand, p2);   // global-memory sort for very large k (REPL paging)
+            peer_wait_slot(po);
+            emit_sorted(cand, min(count, k_eff), k, ids, D, I);
+        }
+        peer_signal(po, 1u);
+        // every other block is done with this query: reset histograms + selection state for the next search
+        // (ws[0] also carries the grid barrier counter: no barrier follows phase 2)
         __syncthreads();
+        uint32_t *wz = reinterpret_cast<uint32_t *>(w);
+        for (uint32_t i = threadIdx.x; i < sizeof(QueryWs) / 4; i += blockDim.x) wz[i] = 0u;
+        __syncthreads();
+        if (q == nq_valid - 1) stamp(3);
     }
-    uint32_t p2 = 1;
-    while (p2 < count) p2 <<= 1;
-    float *D = D_all + (size_t)blockIdx.y * k;
-    int64_t *I = I_all + (size_t)blockIdx.y * k;
-    if (p2 <= (uint32_t)kSortSmem) {
-        for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) s_sort[i] = i < count ? __ldcg(cand + i) : 0ull;
-        __syncthreads();
-        bitonic_desc(s_sort, p2);
-        peer_wait_slot(po);
-        emit_sorted(s_sort, count, k, ids, D, I);
-    } else {
-        for (uint32_t i = count + threadIdx.x; i < p2; i += blockDim.x) cand[i] = 0ull;
-        __syncthreads();
-        bitonic_desc(cand, p2);   // global-memory sort for very large k (REPL paging)
-        peer_wait_slot(po);
-        emit_sorted(cand, count, k, ids, D, I);
-    }
-    peer_signal(po, 1u);
-    // every other block of this query has retired: reset histograms + selection state for the next search
-    uint32_t *wz = reinterpret_cast<uint32_t *>(w);
-    for (uint32_t i = threadIdx.x; i < sizeof(QueryWs) / 4; i += blockDim.x) wz[i] = 0u;
 }
 
 // empty shard: every slot is padding.  One block, so it can take part in the peer protocol.
@@ -573,6 +678,7 @@ struct cb_index {
     static constexpr int kEv = 256;
     cudaEvent_t ev0[kEv] = {nullptr}, ev1[kEv] = {nullptr};
     int ev_n = 0;
+    unsigned long long *phase_t = nullptr;   // device: 4 %globaltimer stamps of the most recent timed launch
 
     size_t row_bytes() const { return (size_t)d * (dtype == CB_F16 ? 2 : 4); }
     IdMap idmap(int64_t id_base) const {
@@ -626,9 +732,11 @@ static int ensure_ws(cb_index *ix, int64_t k_eff) {
 }
 
 template <int NQ, bool F16>
-static int launch_scan(cb_index *ix, const float *q_dev, int nq_valid, uint32_t k_eff, cudaStream_t s) {
-    auto kern = flatip_scan_kernel<NQ, F16>;
-    const size_t smem = (size_t)NQ * kBins0 * sizeof(uint32_t);
+static int launch_search(cb_index *ix, const float *q_dev, int nq_valid, uint32_t k_eff, int64_t k, float *D_dev,
+                         int64_t *I_dev, const IdMap &ids, const PeerOut &po, cudaStream_t s) {
+    auto kern = flatip_search_kernel<NQ, F16>;
+    // phase 1 histograms, later reused as the sort buffer of the last block
+    const size_t smem = std::max<size_t>((size_t)NQ * kBins0 * sizeof(uint32_t), (size_t)kSortSmem * sizeof(uint64_t));
     constexpr int slot = NQ == 1 ? 0 : NQ == 2 ? 1 : 2;
     int &bps = ix->scan_blocks_per_sm[F16 ? 1 : 0][slot];
     if (bps == 0) {
@@ -639,6 +747,7 @@ static int launch_scan(cb_index *ix, const float *q_dev, int nq_valid, uint32_t 
     constexpr int R = F16 ? 8 : 4;
     int64_t groups = (ix->ntotal + R - 1) / R;
     int64_t want = (groups + (kScanThreads / 32) - 1) / (kScanThreads / 32);
+    // cooperative launch: every block is resident (the kernel has grid-wide barriers)
     int grid = (int)std::min<int64_t>((int64_t)ix->sms * bps, std::max<int64_t>(want, 1));
     const bool timed = ix->timing && ix->ev_n < cb_index::kEv;
     if (timed) {
@@ -648,8 +757,26 @@ static int launch_scan(cb_index *ix, const float *q_dev, int nq_valid, uint32_t 
         }
         CB_CUDA(cudaEventRecord(ix->ev0[ix->ev_n], s));
     }
-    kern<<<grid, kScanThreads, smem, s>>>((const uint4 *)ix->rows, ix->ntotal, q_dev, nq_valid,
-                                           ix->scores, ix->score_stride, ix->ws, k_eff);
+    const uint4 *rows = (const uint4 *)ix->rows;
+    int64_t n = ix->ntotal, stride = ix->score_stride;
+    float *scores = ix->scores;
+    QueryWs *ws = ix->ws;
+    uint64_t *cand = ix->cand;
+    uint32_t cand_cap = ix->cand_cap;
+    const float *mx = ix->max_norm2;
+    IdMap ids_v = ids;
+    PeerOut po_v = po;
+    unsigned long long *phase_t = nullptr;
+    if (ix->timing) {
+        if (!ix->phase_t) {
+            CB_CUDA(cudaMalloc(&ix->phase_t, 64));
+            CB_CUDA(cudaMemset(ix->phase_t, 0, 64));
+        }
+        phase_t = ix->phase_t;
+    }
+    void *args[] = {&rows, &n, &q_dev, &nq_valid, &scores, &stride, &ws, &k_eff, &k, &cand, &cand_cap, &mx,
+                    &ids_v, &po_v, &D_dev, &I_dev, &phase_t};
+    CB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kScanThreads), args, smem, s));
     CB_LAUNCH_CHECK();
     if (timed) {
         CB_CUDA(cudaEventRecord(ix->ev1[ix->ev_n], s));
@@ -658,32 +785,24 @@ static int launch_scan(cb_index *ix, const float *q_dev, int nq_valid, uint32_t 
     return CB_OK;
 }
 
-// one pass of the streaming path over <= kMaxNQ queries: scan, 2 x refine, collect
+// the streaming path over <= kMaxNQ queries: ONE cooperative launch (scan + select + write)
 static int search_tile(cb_index *ix, int nq, const float *q_dev, int64_t k, float *D_dev,
                        int64_t *I_dev, const IdMap &ids, const PeerOut &po, cudaStream_t s) {
     const int64_t n = ix->ntotal;
-    const int64_t k_eff = std::min<int64_t>(k, n);
-    // histograms + state are zero between searches: the collect kernel's last block re-zeroes them
-    // (k_rem is seeded by the scan kernel's last block).  Only a search that failed half way needs a memset.
+    const uint32_t k_eff = (uint32_t)std::min<int64_t>(k, n);
+    // histograms + state are zero between searches: the kernel's last block re-zeroes them.  Only a search
+    // that failed half way needs a memset.
     if (ix->ws_dirty) CB_CUDA(cudaMemsetAsync(ix->ws, 0, sizeof(QueryWs) * kMaxNQ, s));
     ix->ws_dirty = true;
     const bool f16 = ix->dtype == CB_F16;
     int rc;
-    if (nq == 1) rc = f16 ? launch_scan<1, true>(ix, q_dev, nq, (uint32_t)k_eff, s) : launch_scan<1, false>(ix, q_dev, nq, (uint32_t)k_eff, s);
-    else if (nq == 2) rc = f16 ? launch_scan<2, true>(ix, q_dev, nq, (uint32_t)k_eff, s) : launch_scan<2, false>(ix, q_dev, nq, (uint32_t)k_eff, s);
-    else rc = f16 ? launch_scan<4, true>(ix, q_dev, nq, (uint32_t)k_eff, s) : launch_scan<4, false>(ix, q_dev, nq, (uint32_t)k_eff, s);
+    if (nq == 1) rc = f16 ? launch_search<1, true>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
+                          : launch_search<1, false>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
+    else if (nq == 2) rc = f16 ? launch_search<2, true>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
+                               : launch_search<2, false>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
+    else rc = f16 ? launch_search<4, true>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
+                  : launch_search<4, false>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
     if (rc) return rc;
-
-    const int64_t n4 = (n + 3) / 4;
-    int gx = (int)std::min<int64_t>((int64_t)ix->sms * 4, std::max<int64_t>((n4 + kPostThreads - 1) / kPostThreads, 1));
-    dim3 grid(gx, nq);
-    for (int pass = 1; pass <= 2; pass++) {
-        flatip_refine_kernel<<<grid, kPostThreads, 0, s>>>(ix->scores, n, ix->score_stride, ix->ws, pass);
-        CB_LAUNCH_CHECK();
-    }
-    flatip_collect_kernel<<<grid, kPostThreads, 0, s>>>(ix->scores, n, ix->score_stride, ix->ws, ix->cand,
-                                                        ix->cand_cap, k, ids, po, D_dev, I_dev);
-    CB_LAUNCH_CHECK();
     ix->ws_dirty = false;
     return CB_OK;
 }
@@ -884,7 +1003,7 @@ void cb_flatip_free(cb_index *ix) {
     p2p_detach(ix);
     cudaFree(ix->rows); cudaFree(ix->scores); cudaFree(ix->ws); cudaFree(ix->cand);
     cudaFree(ix->d_q); cudaFree(ix->d_D); cudaFree(ix->d_I); cudaFree(ix->d_stage);
-    cudaFree(ix->max_norm2); cudaFree(ix->seg_dev);
+    cudaFree(ix->max_norm2); cudaFree(ix->seg_dev); cudaFree(ix->phase_t);
     cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_D); cudaFreeHost(ix->h_I);
     cb::batch_ws_delete(ix->bws);
     for (int i = 0; i < cb_index::kEv; i++) {
@@ -1146,6 +1265,21 @@ int cb_flatip_timing_read(cb_index *ix, double *scan_ms_total, int *n_scans) {
     *scan_ms_total = tot;
     *n_scans = ix->ev_n;
     ix->ev_n = 0;
+    return CB_OK;
+}
+
+int cb_flatip_phase_times(cb_index *ix, double *ms3) {
+    CB_REQUIRE(ix && ms3, "cb_flatip_phase_times: null argument");
+    ms3[0] = ms3[1] = ms3[2] = 0;
+    if (!ix->phase_t) return CB_OK;
+    DeviceGuard g(ix->device);
+    unsigned long long t[4];
+    CB_CUDA(cudaMemcpy(t, ix->phase_t, sizeof(t), cudaMemcpyDeviceToHost));
+    if (t[3] >= t[2] && t[2] >= t[1] && t[1] >= t[0]) {
+        ms3[0] = (double)(t[1] - t[0]) * 1e-6;
+        ms3[1] = (double)(t[2] - t[1]) * 1e-6;
+        ms3[2] = (double)(t[3] - t[2]) * 1e-6;
+    }
     return CB_OK;
 }
 

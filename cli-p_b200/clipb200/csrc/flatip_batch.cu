@@ -13,8 +13,8 @@
 //            thr is the exact k-th best so far; margin = (2^-11 + 2^-16) |q| max|x| + 1e-6 bounds
 //            |<q - fp16(q), x>| plus the tensor core's accumulation error, so no row whose exact
 //            score beats thr is ever dropped.
-//   RE-SCORE between row ranges (they grow 1K, +8K, +64K ... so the expected survivors per range
-//            stay ~7k), one block per query computes the EXACT fp32 score of every new candidate
+//   RE-SCORE between row ranges (they grow 1K, +8K, +64K ... at k <= 256, slower for larger k, so the
+//            expected survivors per range stay a small multiple of k), one block per query computes the EXACT fp32 score of every new candidate
 //            with the same summation order as the streaming scan (flatip.cuh): batch and scan
 //            answers are bit-identical, scores included.  It then sorts by (score desc, id asc),
 //            keeps k and raises thr.  Ranges ascend in id, so ties resolve exactly.
@@ -525,8 +525,10 @@ static int search_group(BatchWs *w, const void *rows_f16, int64_t n, int sms, in
     int rc;
     if ((rc = make_map(&tmQ, w->qh, (uint64_t)nq_pad, kD, QM))) return rc;
     if ((rc = make_map(&tmX, rows_f16, (uint64_t)n, kD, RN / ncta))) return rc;
-    // row ranges grow geometrically (x8) so the expected survivors per range stay ~7k (k m / n_seen); few
-    // queries can afford longer ranges (fewer launches on the HBM-bound small-nq pass)
+    // row ranges grow geometrically (x g): the expected survivors of a range are k m / n_seen ~ (g - 1) k, and
+    // they must stay well inside the kCap slots next to the k kept entries: g = 8 up to k = 256, 2 at k = 1024.
+    // Few queries can afford longer ranges (fewer launches on the HBM-bound small-nq pass)
+    const int64_t growth = std::max<int64_t>(2, std::min<int64_t>(8, kCap / (4 * k)));
     const int64_t span_max = nq <= QM ? (16ll << 20) : (4ll << 20);
     int64_t r0 = 0, span = 1024;
     while (r0 < n) {
@@ -547,7 +549,7 @@ static int search_group(BatchWs *w, const void *rows_f16, int64_t n, int sms, in
                 r1, final_pass, ids, po, D_dev, I_dev, w->rescued);
         CB_LAUNCH_CHECK();
         r0 = r1;
-        span = std::min<int64_t>(span * 8, span_max);
+        span = std::min<int64_t>(span * growth, span_max);
     }
     return CB_OK;
 }

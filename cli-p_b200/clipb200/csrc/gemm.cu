@@ -246,7 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (kTmaStore && EPI == EPI_BIAS_RESID) {
                 // the residual prefetch below overwrites every staging box: the previous tile's bulk
                 // stores must have finished reading them
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
             }
             // -- before the accumulator is ready: stage bias and (coalesced, async) the residual
@@ -305,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (kTmaStore && EPI != EPI_BIAS_RESID) {
                     // box c is rewritten below: its bulk store of the previous tile (one group per box, so
                     // NB - 1 younger groups may still be pending) must have finished reading it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBOX - 1) : "memory");
+                    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBOX - 1) : "memory");
                     __syncwarp();
                 }
                 uint32_t v[32];
@@ -402,7 +402,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // per box so the next tile can reuse box c while later boxes are still in flight
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) {
+                        // one elected lane (always the same one: bulk groups are per thread) issues the store;
+                        // behind elect.sync the tensor-map address and coordinates stay in uniform registers
+                        if (elect_one()) {
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                          ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(stage_base + (c % NBOX) * C::EPI_BOX_BYTES),
                                            "r"(n0), "r"(row0)
@@ -417,7 +419,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
                 if (NCTA == 1) mbar_arrive_relaxed(&tempty[as]);
                 else mbar_arrive_cluster(&tempty[as], 0);    // the leader's MMA warp waits for both CTAs
             }
@@ -438,7 +440,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
         if (kTmaStore) {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             __syncwarp();
         }
     }

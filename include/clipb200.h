@@ -159,12 +159,16 @@ int cb_flatip_get_rows(cb_index *ix, int64_t start, int64_t n, float *out_host);
  * dtype) -- for zero-copy ingest checks and benches */
 const void *cb_flatip_device_rows(const cb_index *ix);
 
-/* Live timing of the scan kernel (the dominant kernel of a search): when enabled,
- * every scan launch is bracketed by CUDA events on its own stream (up to 256
- * launches); timing_read waits for them, returns the summed duration and count
+/* Live timing of the search kernel (scan + select in one cooperative launch; the dominant
+ * kernel of a search): when enabled, every launch is bracketed by CUDA events on its own stream
+ * (up to 256 launches); timing_read waits for them, returns the summed duration and count
  * and clears the list.  Used by bench.py for the roofline figure. */
 int cb_flatip_timing(cb_index *ix, int enable);
 int cb_flatip_timing_read(cb_index *ix, double *scan_ms_total, int *n_scans);
+/* phases of the most recent timed launch of the search kernel, from %globaltimer stamps inside it:
+ * ms3 = {pass over the shard up to the grid barrier, k-th-bin decision (+ radix levels if any),
+ * gather + sort + write}.  Synchronises. */
+int cb_flatip_phase_times(cb_index *ix, double *ms3);
 
 /* ---- CLIP ViT-B/32 towers (replaces `import clip`'s model) ----------------- */
 typedef struct cb_clip cb_clip;

@@ -1,12 +1,14 @@
 """Where the tower GEMMs' time goes, per shape (run on the GPU box):
   full      the shipped kernel (tile picked by pick_config)
-  nostore   CLIPB200_GEMM_DEBUG=2: everything but the epilogue's TMA bulk stores
-  mainloop  CLIPB200_GEMM_DEBUG=1: TMA + MMA only (epilogue warps just release the accumulator)
-  A-only    CLIPB200_GEMM_DEBUG=3: full kernel, but W tiles are loaded for a cluster's first tile only (the
+  nostore   gemm_debug=2: everything but the epilogue's TMA bulk stores
+  mainloop  gemm_debug=1: TMA + MMA only (epilogue warps just release the accumulator)
+  A-only    gemm_debug=3: full kernel, but W tiles are loaded for a cluster's first tile only (the
             operand traffic a W-stationary schedule would have; results are garbage)
-  A-only+mainloop  CLIPB200_GEMM_DEBUG=5: both of the above (is the mainloop bound by operand delivery?)
+  A-only+mainloop  gemm_debug=5: both of the above (is the mainloop bound by operand delivery?)
   cublas    torch's fp16 matmul (cuBLASLt) on the same operands, bias/activation/residual NOT included
-CUDA events, 30 launches each after 5 warm-ups."""
+CUDA events, 30 launches each after 5 warm-ups.  The gemm_debug probes corrupt results and exist only in
+the experiments build:  python -m clipb200.build --experiments;  CLIPB200_LIB=<...>/libclipb200_exp.so python
+profiles/gemm_decompose.py.  With the product library only `full` and `cublas` are reported."""
 import ctypes as C
 import os
 import sys
@@ -50,24 +52,20 @@ for (M, Nn, K, epi, name) in SHAPES:
 
     fl = 2 * M * Nn * K / 1e9
     line = f"{name:16s} M={M} N={Nn} K={K} epi={epi}:"
-    for label, dbg in (("full", None), ("nostore", "2"), ("mainloop", "1"), ("A-only", "3"), ("A-only+mainloop", "5")):
-        if dbg is None:
-            os.environ.pop("CLIPB200_GEMM_DEBUG", None)
-        else:
-            os.environ["CLIPB200_GEMM_DEBUG"] = dbg
+    HAVE_DBG = N.lib().cb_tuning_set(b"gemm_debug", -1) == 0
+    variants = (("full", -1), ("nostore", 2), ("mainloop", 1), ("A-only", 3), ("A-only+mainloop", 5)) if HAVE_DBG else (("full", -1),)
+    for label, dbg in variants:
+        if HAVE_DBG:
+            N.tuning_set("gemm_debug", dbg)
         ms = timeit(run)
         line += f"  {label} {ms * 1e3:6.1f}us {fl / ms:5.0f}TF"
-    if Nn % 192 == 0:
-        os.environ["CLIPB200_GEMM_BN"] = "192"
-        for label, dbg in (("full192", None), ("A-only192", "3")):
-            if dbg is None:
-                os.environ.pop("CLIPB200_GEMM_DEBUG", None)
-            else:
-                os.environ["CLIPB200_GEMM_DEBUG"] = dbg
-            ms = timeit(run)
-            line += f"  {label} {ms * 1e3:6.1f}us {fl / ms:5.0f}TF"
-        os.environ.pop("CLIPB200_GEMM_BN", None)
-    os.environ.pop("CLIPB200_GEMM_DEBUG", None)
+    for bn in (128, 192, 256):
+        if Nn % bn == 0:
+            with N.tuning(gemm_bn=bn):
+                ms = timeit(run)
+            line += f"  bn{bn} {ms * 1e3:6.1f}us"
+    if HAVE_DBG:
+        N.tuning_set("gemm_debug", -1)
     Wt = W.t()
     o2 = torch.empty((M, Nn), dtype=torch.float16, device="cuda")
     ms = timeit(lambda: torch.matmul(A, Wt, out=o2))

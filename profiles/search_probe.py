@@ -47,6 +47,23 @@ def main():
             if mode != "scan":
                 line += f" ({2.0 * nq * n * 512 / ms / 1e9:7.1f} TFLOP/s, {n * 1024 / ms / 1e6:6.0f} GB/s)"
         print(line, flush=True)
+    # phases inside the single-query search kernel
+    import ctypes as C
+    L = _native.lib()
+    h = index._shards[0].handle
+    q = synth.device_unit_rows(1, 512, seed=8, device=dev, dtype=torch.float32)
+    L.cb_flatip_timing(h, 1)
+    for k in (100, 1000, 5000):
+        acc = [0.0, 0.0, 0.0]
+        for _ in range(5):
+            with _native.tuning(batch_min_nq=1 << 30):
+                index.search_device(q, k)
+            torch.cuda.synchronize()
+            ms3 = (C.c_double * 3)()
+            L.cb_flatip_phase_times(h, ms3)
+            acc = [a + b / 5 for a, b in zip(acc, ms3)]
+        print(f"nq=1 k={k}: scan pass {acc[0] * 1e3:8.1f} us   decide {acc[1] * 1e3:7.1f} us   gather+sort+write {acc[2] * 1e3:7.1f} us")
+    L.cb_flatip_timing(h, 0)
 
 
 if __name__ == "__main__":
