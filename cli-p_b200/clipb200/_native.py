@@ -84,6 +84,7 @@ SIGNATURES = {
     "cb_clip_encode_text": (_int, [_p, _i64, _p, _p, _int]),
     "cb_clip_timing": (_int, [_p, _int]),
     "cb_clip_timing_breakdown": (_int, [_p, C.POINTER(C.c_double)]),
+    "cb_clip_timing_launches": (_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), _int, C.POINTER(_int)]),
     "cb_clip_timing_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_int)]),
     "cb_layernorm_f16_device": (_int, [_p, _p, _p, _p, _int, _int, _int, _p, _p, _int, _p]),
     "cb_attention_f16_device": (_int, [_p, _p, _int, _int, _int, _int, _p]),

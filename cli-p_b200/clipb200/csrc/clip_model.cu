@@ -913,6 +913,21 @@ int cb_clip_timing_breakdown(cb_clip *m, double *ms_by_class4) {
     return CB_OK;
 }
 
+int cb_clip_timing_launches(cb_clip *m, double *ms_out, double *t0_ms_out, int cap, int *n) {
+    CB_REQUIRE(m && ms_out && t0_ms_out && n, "cb_clip_timing_launches: null argument");
+    DeviceGuard g(m->device);
+    CB_CUDA(cudaDeviceSynchronize());
+    *n = std::min(cap, m->stamp_n);
+    if (*n <= 0) { *n = 0; return CB_OK; }
+    std::vector<unsigned long long> st((size_t)*n * 2);
+    CB_CUDA(cudaMemcpy(st.data(), m->stamps, st.size() * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < *n; i++) {
+        ms_out[i] = st[2 * i + 1] >= st[2 * i] ? (double)(st[2 * i + 1] - st[2 * i]) * 1e-6 : -1.0;
+        t0_ms_out[i] = (double)(st[2 * i] - st[0]) * 1e-6;
+    }
+    return CB_OK;
+}
+
 int cb_clip_timing_read(cb_clip *m, double *gemm_ms_total, double *gemm_flops, int *n_gemms) {
     CB_REQUIRE(m && gemm_ms_total && gemm_flops && n_gemms, "cb_clip_timing_read: null argument");
     DeviceGuard g(m->device);

@@ -95,6 +95,40 @@ __device__ void find_bin(const uint32_t *hist, int nbins, int digit_bits, SelSta
     __syncwarp();
 }
 
+// the same over a histogram already in shared memory (no dependent L2 round trips)
+__device__ void find_bin_smem(const uint32_t *hist, int nbins, int digit_bits, SelState *st) {
+    const int lane = threadIdx.x & 31;
+    const int per = nbins / 32;
+    const int hi = nbins - 1 - lane * per;
+    uint32_t s = 0;
+    for (int i = 0; i < per; i++) s += hist[hi - i];
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - s;
+    const uint32_t k_rem = st->k_rem;
+    __syncwarp();
+    if (excl < k_rem && incl >= k_rem) {
+        uint32_t acc = excl;
+        for (int i = 0; i < per; i++) {
+            uint32_t c = hist[hi - i];
+            if (acc + c >= k_rem) {
+                st->prefix = (st->prefix << digit_bits) | (uint32_t)(hi - i);
+                st->bits += digit_bits;
+                st->k_rem = k_rem - acc;
+                st->cnt_bin = c;
+                st->done = (c == k_rem - acc) ? 1u : 0u;
+                break;
+            }
+            acc += c;
+        }
+    }
+    __syncwarp();
+}
+
 // block-retire ticket: returns true in every thread of the last block to arrive
 __device__ bool last_block(uint32_t *ticket, uint32_t nblocks) {
     __shared__ bool s_last;
@@ -316,12 +350,18 @@ flatip_search_kernel(const uint4 *__restrict__ xb, int64_t n, const float *__res
     grid_barrier(bar, epoch);
     if (blockIdx.x == 0) stamp(1);
 
-    // ---- phase 2: level-0 decision, computed by every block for itself (2048 counters per query)
+    // ---- phase 2: level-0 decision, computed by every block for itself: the 2048 counters per query
+    // come through L2 in one coalesced round trip into shared memory, then one warp per query scans them
+    for (int i = threadIdx.x; i < nq_valid * kBins0; i += blockDim.x) {
+        const int q = i / kBins0;
+        s_hist[i] = __ldcg(&ws[q].hist[0][i - q * kBins0]);
+    }
+    __syncthreads();
     if (wid < nq_valid && wid < NQ) {
         SelState *l0 = &s_l0[wid];
         if (lane == 0) { l0->prefix = 0; l0->bits = 0; l0->k_rem = k_eff; l0->cnt_bin = 0; l0->done = 0; }
         __syncwarp();
-        find_bin(ws[wid].hist[0], kBins0, 11, l0);
+        find_bin_smem(s_hist + wid * kBins0, kBins0, 11, l0);
     }
     __syncthreads();
     const uint32_t short_cap = min(cand_cap, (uint32_t)kSortSmem);
@@ -555,6 +595,67 @@ topk_merge_kernel(int R, int64_t nq, int64_t k, const float *D_in,
     }
 }
 
+// The same merge without a sort, for R k <= 4096: the lists are already sorted, so an entry's final
+// position is its own index plus, for every other list, the number of entries that come before it
+// there (a binary search).  No barriers between the load and the store; ~50 shared-memory probes per entry.
+__global__ void __launch_bounds__(kPostThreads)
+topk_merge_rank_kernel(int R, int64_t nq, int64_t k, const float *D_in, const int64_t *I_in,
+                       int64_t shard_stride_D, int64_t shard_stride_I, float *D_out, int64_t *I_out,
+                       const MergeSync ms) {
+    extern __shared__ unsigned char s_raw[];
+    if (ms.done) {
+        if (threadIdx.x < (unsigned)R) spin_until(ms.done + threadIdx.x, ms.need_done, ms.error);
+        __syncthreads();
+    }
+    const int64_t q = blockIdx.x;
+    const uint32_t kk = (uint32_t)k, tot = (uint32_t)R * kk;
+    int64_t *si = reinterpret_cast<int64_t *>(s_raw);
+    float *ss = reinterpret_cast<float *>(si + tot);
+    for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) {
+        const uint32_t r = i / kk, j = i - r * kk;
+        const size_t src = (size_t)q * k + j;
+        ss[i] = __ldcg(D_in + (size_t)r * shard_stride_D + src);    // L2: peers wrote these lines
+        si[i] = __ldcg(I_in + (size_t)r * shard_stride_I + src);
+    }
+    for (int64_t j = threadIdx.x; j < k; j += blockDim.x) {         // padding first; winners overwrite it
+        D_out[q * k + j] = -3.4028234663852886e38f;
+        I_out[q * k + j] = -1;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) {
+        const float s = ss[i];
+        const int64_t id = si[i];
+        if (id < 0) continue;                                       // padding of a short shard
+        const uint32_t r = i / kk;
+        uint32_t rank = i - r * kk;                                 // everything before it in its own list is valid
+        for (uint32_t o = 0; o < (uint32_t)R; o++) {
+            if (o == r) continue;
+            // entries of list o that come before (s, id): valid, and higher score or equal score with a lower id
+            uint32_t lo = 0, hi = kk;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const float so = ss[o * kk + mid];
+                const int64_t io = si[o * kk + mid];
+                const bool before = io >= 0 && (so > s || (so == s && io < id));
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < kk) {
+            D_out[q * k + rank] = s;
+            I_out[q * k + rank] = id;
+        }
+    }
+    if (ms.consumed) {
+        // this query's slot lines have been read (they sit in ss / si): let the peers reuse them
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            red_release_sys_add(ms.consumed, 1u);
+        }
+    }
+}
+
 // max over rows of ||x||^2 (as stored), kept per shard: bounds |<q - fp16(q), x>| in the batch path
 template <bool F16>
 __global__ void rownorm_max_kernel(const uint4 *__restrict__ rows, int64_t n, float *max_norm2) {
@@ -720,8 +821,10 @@ static int ensure_ws(cb_index *ix, int64_t k_eff) {
         CB_CUDA(cudaMalloc(&ix->ws, sizeof(QueryWs) * kMaxNQ));
         ix->ws_dirty = true;
     }
+    // room for the short list (everything in the bins at or above the k-th score's bin: k plus a bin's worth
+    // of rows) as long as it can still be sorted in shared memory; never less than k
     uint32_t p2 = 256;
-    while ((int64_t)p2 < k_eff) p2 <<= 1;
+    while ((int64_t)p2 < std::min<int64_t>(2 * k_eff, kSortSmem) || (int64_t)p2 < k_eff) p2 <<= 1;
     if (p2 > ix->cand_cap) {
         if (ix->cand) CB_CUDA(cudaFree(ix->cand));
         ix->cand = nullptr;
@@ -844,6 +947,13 @@ static int search_core(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, 
 
 static int launch_merge(int R, int64_t nq, int64_t k, const float *D_in, const int64_t *I_in, int64_t shard_stride_D,
                         int64_t shard_stride_I, float *D_out, int64_t *I_out, const MergeSync &ms, cudaStream_t s) {
+    if ((int64_t)R * k <= 4096) {
+        // sorted lists, few entries: place every entry by rank (no sort, no barriers)
+        topk_merge_rank_kernel<<<(unsigned)nq, kPostThreads, (size_t)R * k * 12, s>>>(
+            R, nq, k, D_in, I_in, shard_stride_D, shard_stride_I, D_out, I_out, ms);
+        CB_LAUNCH_CHECK();
+        return CB_OK;
+    }
     uint32_t p2 = 2;
     while ((int64_t)p2 < (int64_t)R * k) p2 <<= 1;
     size_t smem = (size_t)p2 * 12;

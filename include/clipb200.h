@@ -235,6 +235,9 @@ int cb_clip_encode_text(cb_clip *m, int64_t B, const int32_t *ids_host, float *o
  * CUDA-event duration, algorithmic FLOPs (2*M*N*K) and count since enable/read */
 int cb_clip_timing(cb_clip *m, int enable);   /* 0 off, 1 GEMM launches, 2 every kernel class */
 int cb_clip_timing_read(cb_clip *m, double *gemm_ms_total, double *gemm_flops, int *n_gemms);
+/* call before cb_clip_timing_read: per timed GEMM launch, in launch order, its device-side duration
+ * and its start relative to the first one (ms) */
+int cb_clip_timing_launches(cb_clip *m, double *ms_out, double *t0_ms_out, int cap, int *n);
 /* call before cb_clip_timing_read: summed live duration per kernel class since enable,
  * ms_by_class4 = {gemm, attention, layernorm, other} (level 2 only for the last three) */
 int cb_clip_timing_breakdown(cb_clip *m, double *ms_by_class4);
