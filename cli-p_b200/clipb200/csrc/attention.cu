@@ -53,6 +53,7 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int W = heads * HD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();                     // qkv comes from the previous kernel of the stream (common.cuh)
 
     // stage q|k|v of this head: 3 x LP rows x 8 chunks of 16 B, global -> shared with cp.async (no register
     // round trip); rows >= L of V are zero.  blockDim = 8 chunks x (4 KT) rows, so iteration `it` of the
@@ -156,6 +157,7 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
         if (r0 < L) *reinterpret_cast<uint32_t *>(out + (size_t)(b * L + r0) * W + col) = pack2(o[dt][0] * i0, o[dt][1] * i0);
         if (r1 < L) *reinterpret_cast<uint32_t *>(out + (size_t)(b * L + r1) * W + col) = pack2(o[dt][2] * i1, o[dt][3] * i1);
     }
+    pdl_launch_dependents();
 }
 
 }  // namespace
@@ -163,13 +165,13 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
 int attention_f16(const __half *qkv, __half *out, int B, int L, int heads, bool causal, cudaStream_t s) {
     if (B == 0) return CB_OK;
     if (L == 50 && !causal) {
-        attention_kernel<50, false><<<B * heads, 4 * 32, 0, s>>>(qkv, out, heads);
+        CB_CUDA(launch_ex(attention_kernel<50, false>, dim3(B * heads), dim3(4 * 32), 0, s, 1, true, qkv, out, heads));
     } else if (L == 77 && causal) {
-        attention_kernel<77, true><<<B * heads, 5 * 32, 0, s>>>(qkv, out, heads);
+        CB_CUDA(launch_ex(attention_kernel<77, true>, dim3(B * heads), dim3(5 * 32), 0, s, 1, true, qkv, out, heads));
     } else if (L == 77 && !causal) {
-        attention_kernel<77, false><<<B * heads, 5 * 32, 0, s>>>(qkv, out, heads);
+        CB_CUDA(launch_ex(attention_kernel<77, false>, dim3(B * heads), dim3(5 * 32), 0, s, 1, true, qkv, out, heads));
     } else if (L == 50 && causal) {
-        attention_kernel<50, true><<<B * heads, 4 * 32, 0, s>>>(qkv, out, heads);
+        CB_CUDA(launch_ex(attention_kernel<50, true>, dim3(B * heads), dim3(4 * 32), 0, s, 1, true, qkv, out, heads));
     } else {
         set_error("attention_f16: sequence length %d not supported (50 or 77)", L);
         return CB_ERR_INVALID;

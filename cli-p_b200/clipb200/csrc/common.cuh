@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 #include "../../../include/clipb200.h"
 
@@ -28,7 +29,7 @@ enum Tune : int {
                           //                             unset: fold, checked by the calibration pass of cb_clip_finalize
     T_GEMM_DEBUG,         // CLIPB200_GEMM_DEBUG         (only in -DCLIPB200_EXPERIMENTS builds) result-corrupting probes
     T_SKIP,               // CLIPB200_SKIP               (only in -DCLIPB200_EXPERIMENTS builds)
-    T_SEARCH_LINBINS,     // CLIPB200_SEARCH_LINBINS     0: first-level radix on float bits instead of linear score bins
+    T_PDL,                // CLIPB200_PDL                0: no programmatic dependent launch between the towers' kernels
     T_COUNT
 };
 int64_t tune(Tune t);
@@ -78,6 +79,49 @@ struct DeviceGuard {
     }
     int cur = -1;
 };
+
+// ---- programmatic dependent launch -------------------------------------------------------
+// The towers are chains of ~70 short kernels on one stream.  Launched with the programmatic-serialization
+// attribute, a kernel's CTAs may be scheduled while its predecessor is still draining: their prologue
+// (barrier init, TMEM allocation, descriptor prefetch, LUTs) overlaps the predecessor's tail, and the
+// launch latency disappears from the critical path.  Every such kernel calls pdl_wait() before it touches
+// global memory (it returns once the predecessor grid has completed and its writes are visible) and
+// pdl_launch_dependents() to let its own successor be scheduled.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// launch with optional cluster dimension and (unless the pdl knob is 0 or the stream is being captured
+// into a CUDA graph) the programmatic-serialization attribute
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
+                      bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster_x > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster_x;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    if (pdl && tune(T_PDL) != 0) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
+        if (cs == cudaStreamCaptureStatusNone) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            na++;
+        }
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- device helpers -------------------------------------------------------
 

@@ -272,10 +272,13 @@ flatip_search_kernel(const uint4 *__restrict__ xb, int64_t n, const float *__res
     __shared__ uint32_t s_warp[kScanThreads / 32];
     __shared__ uint32_t s_filled;
     __shared__ float s_scale[NQ];
+    __shared__ uint32_t s_slot_free;
     uint32_t *s_hist = s_dyn;
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NQ * kBins0; i += blockDim.x) s_hist[i] = 0;
+    // any block may turn out to be the one that writes the result: probe the mailbox slot now
+    if (threadIdx.x == 32) s_slot_free = peer_slot_probe(po) ? 1u : 0u;
 
     float qreg[NQ][CH * EPC];
     float qscale[NQ];
@@ -493,13 +496,13 @@ flatip_search_kernel(const uint4 *__restrict__ xb, int64_t n, const float *__res
             for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) s_sort[i] = i < count ? __ldcg(cand + i) : 0ull;
             __syncthreads();
             bitonic_desc(s_sort, p2);
-            peer_wait_slot(po);
+            peer_wait_slot(po, s_slot_free != 0);
             emit_sorted(s_sort, min(count, k_eff), k, ids, D, I);
         } else {
             for (uint32_t i = count + threadIdx.x; i < p2; i += blockDim.x) cand[i] = 0ull;
             __syncthreads();
             bitonic_desc(cand, p2);   // global-memory sort for very large k (REPL paging)
-            peer_wait_slot(po);
+            peer_wait_slot(po, s_slot_free != 0);
             emit_sorted(cand, min(count, k_eff), k, ids, D, I);
         }
         peer_signal(po, 1u);

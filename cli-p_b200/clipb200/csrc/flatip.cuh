@@ -69,11 +69,19 @@ __device__ __forceinline__ void spin_until(const uint32_t *ctr, uint32_t need, u
         }
     }
 }
-// whole block: wait until the destination slot may be overwritten (call before writing D / I)
-__device__ __forceinline__ void peer_wait_slot(const PeerOut &po) {
+// whole block: wait until the destination slot may be overwritten (call before writing D / I).
+// `already_free`: an earlier probe (peer_slot_probe) saw the slot free -- the counter only grows, so
+// the NVLink round trip is skipped.
+__device__ __forceinline__ void peer_wait_slot(const PeerOut &po, bool already_free = false) {
     if (po.done == nullptr) return;
-    if (threadIdx.x == 0) spin_until(po.consumed, po.need_consumed, po.error);
+    if (threadIdx.x == 0 && !already_free) spin_until(po.consumed, po.need_consumed, po.error);
     __syncthreads();
+}
+// one thread, non-blocking: is the destination slot free already?  Issued at kernel entry so that the
+// remote read overlaps the pass over the shard instead of sitting on the critical path at its end.
+__device__ __forceinline__ bool peer_slot_probe(const PeerOut &po) {
+    if (po.done == nullptr) return true;
+    return (int32_t)(ld_acquire_sys(po.consumed) - po.need_consumed) >= 0;
 }
 // whole block: publish `n` finished queries (call after the block's last D / I store)
 __device__ __forceinline__ void peer_signal(const PeerOut &po, uint32_t n) {

@@ -105,27 +105,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int cluster_id = blockIdx.x / NCTA, num_clusters = gridDim.x / NCTA;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
-    uint64_t *empty = full + C::STAGES;
-    uint64_t *tfull = empty + C::STAGES;
+    // the ring depth is a launch parameter: the shared-memory layout follows it, so a shallower ring really
+    // leaves the rest of the SM's shared memory to co-resident CTAs of other kernels
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + num_stages * C::STAGE_BYTES);
+    uint64_t *empty = full + num_stages;
+    uint64_t *tfull = empty + num_stages;
     uint64_t *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // warp-uniform by construction
     const int lane = threadIdx.x & 31;
 
-    if (g.stamp != nullptr && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMin(g.stamp, t);
-    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < C::STAGES; i++) {
+            for (int i = 0; i < num_stages; i++) {
                 mbar_init(&full[i], 1);
                 mbar_init(&empty[i], 1);
             }
@@ -143,6 +140,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (NCTA > 1) cluster_sync_all();          // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+    // everything above touched only this CTA's shared / tensor memory: under programmatic dependent launch it
+    // ran while the previous kernel of the stream was still draining.  From here on global memory is read.
+    pdl_launch_dependents();
+    pdl_wait();
+    if (g.stamp != nullptr && threadIdx.x == 0) {      // live timing: this launch's work starts here
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(g.stamp, t);
+    }
 
     const int num_tiles = m_tiles * n_tiles;
     const int KB = g.K / BK;
@@ -220,7 +226,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         constexpr int CPR = EC / 8;                      // 16-byte chunks per staged row
         constexpr bool kTmaStore = EPI != EPI_F32 && EPI != EPI_PATCH;
         // staging area starts 1024-byte aligned (TMA + swizzle pattern alignment)
-        const uint32_t stage_area = (smem_u32(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + 1023u) & ~1023u;
+        const uint32_t stage_area = (smem_u32(smem + num_stages * C::STAGE_BYTES + C::BAR_BYTES) + 1023u) & ~1023u;
         constexpr int NBOX = C::NBOX;
         const uint32_t stage_base = stage_area + (uint32_t)(warp - 2) * C::EPI_BOX_BYTES * NBOX;
         const uint32_t bias_smem = stage_area + kEpiWarps * C::EPI_BOX_BYTES * NBOX + (uint32_t)(warp - 2) * EC * 8;
@@ -536,25 +542,15 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int clusters = std::min(m_tiles * n_tiles, sms / NCTA);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * NCTA);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = NCTA;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     int stages = C::STAGES;
     if (tune(T_GEMM_STAGES) > 0) stages = std::max(2, std::min(C::STAGES, (int)tune(T_GEMM_STAGES)));
 #ifdef CLIPB200_EXPERIMENTS
     if (tune(T_GEMM_DEBUG) > 0) stages |= (int)tune(T_GEMM_DEBUG) << 8;
 #endif
     if (tune(T_GEMM_RASTER) > 0) stages |= (int)tune(T_GEMM_RASTER) << 16;
-    CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g, m_tiles, n_tiles, stages));
+    const size_t smem_bytes = (size_t)(stages & 0xff) * C::STAGE_BYTES + C::FIXED;
+    CB_CUDA(launch_ex(kern, dim3(clusters * NCTA), dim3(kThreads), smem_bytes, s, NCTA, true, tmA, tmB, tmC, g, m_tiles,
+                      n_tiles, stages));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

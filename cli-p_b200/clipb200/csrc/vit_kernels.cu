@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t *__res
         lut[c][v] = __float2half_rn(__fdiv_rn(__fdiv_rn((float)v, 255.0f) - mean, sd));
     }
     __syncthreads();
+    pdl_wait();                     // the LUT above needed no global memory (common.cuh)
     const int64_t total = (int64_t)B * 224 * 84;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t *__res
         __half *dst = patches + ((size_t)(b * 49 + gy * 7 + gx)) * 3072 + py * 96 + j * 8;
         *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(h);
     }
+    pdl_launch_dependents();
 }
 
 // one thread = 4 pixels x 3 channels of an NCHW fp32 image
@@ -245,7 +247,7 @@ inline int grid_for(int64_t threads, int block) {
 }  // namespace
 
 int preprocess_u8(const uint8_t *img, __half *patches, int B, cudaStream_t s) {
-    preprocess_u8_kernel<<<grid_for((int64_t)B * 224 * 84, 256), 256, 0, s>>>(img, patches, B);
+    CB_CUDA(launch_ex(preprocess_u8_kernel, dim3(grid_for((int64_t)B * 224 * 84, 256)), dim3(256), 0, s, 1, true, img, patches, B));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

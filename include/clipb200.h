@@ -49,6 +49,7 @@ int cb_device_count(int *n);
  *   no_graph           1: small encode_* calls are never replayed as CUDA graphs
  *   ln_blocks_per_sm   LayerNorm grid size
  *   ln_fold            0 / 1 / unset: see cb_clip_finalize
+ *   pdl                0: the towers' kernels are launched without programmatic dependent launch
  * Result-corrupting perf probes (gemm_debug, skip) exist only in -DCLIPB200_EXPERIMENTS builds. */
 int cb_tuning_set(const char *name, int64_t value);
 int cb_tuning_get(const char *name, int64_t *value);
