@@ -426,13 +426,13 @@ def run_search(args, torch, dist, rank, world, local, model=None):
     if cnt.value:
         scan_s = tot_ms.value / 1e3 / cnt.value
         ach = (hi - lo) * SEARCH_BYTES_PER_ROW / scan_s / 1e9
-        traffic, tmeta = traffic_record("flatip_scan_f16_nq1_10m", "cli-p_b200/clipb200/csrc/flatip.cu")
+        traffic, tmeta = traffic_record("flatip_search_f16_nq1_10m", "cli-p_b200/clipb200/csrc/flatip.cu")
         if (hi - lo) != DB_ROWS:
             traffic, tmeta = None, dict(tmeta, note="capture is of the 10M-row single-GPU launch")
         res["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": tmeta,
                            "algorithmic_bytes": (hi - lo) * SEARCH_BYTES_PER_ROW,
-                           "kernel": "flatip_scan_kernel<1,f16>", "kernel_ms": scan_s * 1e3,
+                           "kernel": "flatip_search_kernel<1,f16> (scan + select + write, one cooperative launch)", "kernel_ms": scan_s * 1e3,
                            "kernel_share_of_step": scan_s / (secs / args.steps),
                            "step_level_frac": (hi - lo) * SEARCH_BYTES_PER_ROW / (secs / args.steps) / 1e9 / peaks["hbm_gbs"],
                            "peak_source": peaks["source"] + " (copy bandwidth, read+write; a pure read stream can exceed it)"}

@@ -13,8 +13,9 @@
 //            thr is the exact k-th best so far; margin = (2^-11 + 2^-16) |q| max|x| + 1e-6 bounds
 //            |<q - fp16(q), x>| plus the tensor core's accumulation error, so no row whose exact
 //            score beats thr is ever dropped.
-//   RE-SCORE between row ranges (they grow 1K, +8K, +64K ... at k <= 256, slower for larger k, so the
-//            expected survivors per range stay a small multiple of k), one block per query computes the EXACT fp32 score of every new candidate
+//   RE-SCORE between row ranges (they grow 1K, x16, x16 ... for k ~ 100, slower for larger k), one
+//            block per query first orders its list by score LOWER bounds, drops what cannot reach
+//            the top k any more, and computes the EXACT fp32 score of the ~k contenders
 //            with the same summation order as the streaming scan (flatip.cuh): batch and scan
 //            answers are bit-identical, scores included.  It then sorts by (score desc, id asc),
 //            keeps k and raises thr.  Ranges ascend in id, so ties resolve exactly.
@@ -341,39 +342,68 @@ batch_compact_kernel(uint64_t *__restrict__ cand, uint32_t *__restrict__ cnt, ui
         c = s_n;
     } else {
         c = c_raw;
-        // exact fp32 score of every new candidate: one warp per row, four rows in flight per warp
-        for (uint32_t i = kp + 4 * wid; i < c; i += 4 * nwarps) {
+        // New candidates carry the tensor cores' score s~ of the fp16-rounded query: the exact score lies in
+        // [s~ - m, s~ + m].  Before any row is fetched, order everything by its LOWER bound (exact score for
+        // the kept entries, s~ - m for the new ones): the k-th largest lower bound T cannot exceed the k-th
+        // largest exact score, so only entries whose UPPER bound reaches T can still make the top k.  That is
+        // ~k entries instead of the ~(g - 1) k that passed the stale threshold: the gather from HBM shrinks by
+        // the range growth factor g.
+        const float m = margin[q];
+        for (uint32_t i = kp + threadIdx.x; i < c; i += THREADS) {
+            const uint64_t e = mine[i];
+            buf[i] = ((uint64_t)f2key(key2f((uint32_t)(e >> 32)) - m) << 32) | (e & 0xffffffffull);
+        }
+        __syncthreads();
+        uint32_t P = c;
+        if (c > (uint32_t)k) {
+            const uint32_t p2a = next_pow2(c);
+            for (uint32_t i = c + threadIdx.x; i < p2a; i += THREADS) buf[i] = 0ull;
+            __syncthreads();
+            sort_desc(buf, p2a);
+            const float cut = key2f((uint32_t)(buf[k - 1] >> 32)) - 2.0f * m;
+            if (threadIdx.x == 0) s_n = c;
+            __syncthreads();
+            // entries are sorted by lower bound: the contenders are a prefix
+            for (uint32_t i = (uint32_t)k + threadIdx.x; i < c; i += THREADS)
+                if (key2f((uint32_t)(buf[i] >> 32)) < cut && !(key2f((uint32_t)(buf[i - 1] >> 32)) < cut)) s_n = i;
+            __syncthreads();
+            P = s_n;
+        }
+        // exact fp32 score of the contenders that are new (their rows lie in this range): one warp per
+        // row, four rows in flight per warp
+        for (uint32_t i0 = 4 * wid; i0 < P; i0 += 4 * nwarps) {
             uint32_t id[4];
+            bool isnew[4];
             uint4 v[4][2];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                id[j] = 0xffffffffu - (uint32_t)mine[min(i + j, c - 1)];
-                const uint4 *p = rows + (size_t)id[j] * 64;
-                v[j][0] = ld_stream_v4(p + lane);
-                v[j][1] = ld_stream_v4(p + lane + 32);
+                const uint32_t i = min(i0 + j, P - 1);
+                id[j] = 0xffffffffu - (uint32_t)buf[i];
+                isnew[j] = (int64_t)id[j] >= r0 && i0 + j < P;
+                if (isnew[j]) {
+                    const uint4 *p = rows + (size_t)id[j] * 64;
+                    v[j][0] = ld_stream_v4(p + lane);
+                    v[j][1] = ld_stream_v4(p + lane + 32);
+                }
             }
-            float sc[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+                if (!isnew[j]) continue;                   // warp-uniform
                 float t = 0.f;
                 t += dot8_h(v[j][0], &qr[0]);
                 t += dot8_h(v[j][1], &qr[8]);
-                sc[j] = t;
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int j = 0; j < 4; j++) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
-            if (lane < 4 && i + lane < c) {
-                const float mys = lane == 0 ? sc[0] : lane == 1 ? sc[1] : lane == 2 ? sc[2] : sc[3];
-                const uint32_t myid = lane == 0 ? id[0] : lane == 1 ? id[1] : lane == 2 ? id[2] : id[3];
-                buf[i + lane] = make_comp(f2key(mys + 0.0f), myid);
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) buf[i0 + j] = make_comp(f2key(t + 0.0f), id[j]);
             }
         }
         __syncthreads();
+        c = P;
     }
     const uint32_t keep = min(c, (uint32_t)k);
-    if (c > kp || final_pass) {
+    {
+        // every entry of buf[0, c) now carries its exact score: final order, and the kept list goes back
+        // to the query's global buffer (new entries may have displaced old ones even when c == kp)
         const uint32_t p2 = next_pow2(c);
         for (uint32_t i = c + threadIdx.x; i < p2; i += THREADS) buf[i] = 0ull;
         __syncthreads();
@@ -526,9 +556,10 @@ static int search_group(BatchWs *w, const void *rows_f16, int64_t n, int sms, in
     if ((rc = make_map(&tmQ, w->qh, (uint64_t)nq_pad, kD, QM))) return rc;
     if ((rc = make_map(&tmX, rows_f16, (uint64_t)n, kD, RN / ncta))) return rc;
     // row ranges grow geometrically (x g): the expected survivors of a range are k m / n_seen ~ (g - 1) k, and
-    // they must stay well inside the kCap slots next to the k kept entries: g = 8 up to k = 256, 2 at k = 1024.
-    // Few queries can afford longer ranges (fewer launches on the HBM-bound small-nq pass)
-    const int64_t growth = std::max<int64_t>(2, std::min<int64_t>(8, kCap / (4 * k)));
+    // together with the k kept entries they should fit the compaction's shared-memory list: g = 16 up to
+    // k = 113, 6 at k = 256, 2 from k = 512.  Few queries can afford longer ranges (fewer launches on the
+    // HBM-bound small-nq pass)
+    const int64_t growth = std::max<int64_t>(2, std::min<int64_t>(16, kSmemCap / k - 2));
     const int64_t span_max = nq <= QM ? (16ll << 20) : (4ll << 20);
     int64_t r0 = 0, span = 1024;
     while (r0 < n) {
