@@ -360,3 +360,13 @@ def test_ln_fold_is_dropped_when_calibration_disagrees(sd, golden_inputs):
     a, b = auto.encode_image(images.cuda()), plain.encode_image(images.cuda())
     assert torch.equal(a, b)
     assert torch.equal(auto.encode_text(tokens.cuda()), plain.encode_text(tokens.cuda()))
+
+
+def test_selfcheck_tool_passes_on_synthetic_weights(capsys):
+    """`python -m clipb200.selfcheck --weights ...` is what a user with the real ViT-B-32.pt runs; here it
+    runs on the seeded weights: both towers against its own fp32 torch reference, folded vs unfolded."""
+    from clipb200 import selfcheck
+    rc = selfcheck.main(["--weights", "synthetic"])
+    out = capsys.readouterr().out
+    assert rc == 0, out
+    assert "LayerNorm fold: kept" in out and "selfcheck: OK" in out
