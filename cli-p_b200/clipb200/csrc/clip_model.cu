@@ -51,6 +51,7 @@ struct Ws {
     float *emb = nullptr;
     int *eot = nullptr;
     float *st1 = nullptr, *st2 = nullptr;   // per-row (sum, sum^2) slices for the folded ln_1 / ln_2
+    float *skinny = nullptr;                // split-K partial tiles of single-row-block GEMMs (gemm.cuh)
 };
 
 constexpr int kMaxStatSlices = 24;      // 768 / 32: the BN = 64 tile of single-row-block GEMMs
@@ -221,9 +222,10 @@ int bind_blocks(cb_clip *m, const char *prefix, int W, LayerW *lw) {
 
 // GEMM launches are timed ON THE DEVICE (every CTA folds %globaltimer into a per-launch (min entry, max
 // exit) pair): the duration of a launch then excludes the host-side gaps that CUDA events bracket in
-int timed_gemm(cb_clip *m, const GemmArgs &g0, cudaStream_t s) {
-    if (!m->timing || m->stamp_n >= cb_clip::kStamps) return gemm_f16(g0, s);
+int timed_gemm(cb_clip *m, const Ws &w, const GemmArgs &g0, cudaStream_t s) {
     GemmArgs g = g0;
+    g.skinny_scratch = w.skinny;
+    if (!m->timing || m->stamp_n >= cb_clip::kStamps) return gemm_f16(g, s);
     g.stamp = m->stamps + 2 * (size_t)m->stamp_n;
     int rc = gemm_f16(g, s);
     if (rc) return rc;
@@ -272,18 +274,18 @@ int run_blocks(cb_clip *m, Ws &w, const LayerW *lw, int W, int heads, int B, int
             int rc;
             GemmArgs g = mk(w.x, lw[i].w_qkv, lw[i].b_qkv, nullptr, w.qkv, rows, 3 * W, W, EPI_BIAS);
             g.ln_stats = w.st1; g.ln_slices = i == 0 ? 1 : res_slices; g.colsum = lw[i].cs_qkv;
-            if ((rc = timed_gemm(m, g, s))) return rc;
+            if ((rc = timed_gemm(m, w, g, s))) return rc;
             if (!(skip & 2))
             if ((rc = timed_other(m, 1, s, [&] { return attention_f16(w.qkv, w.att, B, L, heads, causal, s); }))) return rc;
             g = mk(w.att, lw[i].w_o, lw[i].b_o, w.x, w.x, rows, W, W, EPI_BIAS_RESID);
             g.stats_out = w.st2;
-            if ((rc = timed_gemm(m, g, s))) return rc;
+            if ((rc = timed_gemm(m, w, g, s))) return rc;
             g = mk(w.x, lw[i].w_fc, lw[i].b_fc, nullptr, w.mlp, rows, 4 * W, W, EPI_BIAS_GELU);
             g.ln_stats = w.st2; g.ln_slices = res_slices; g.colsum = lw[i].cs_fc;
-            if ((rc = timed_gemm(m, g, s))) return rc;
+            if ((rc = timed_gemm(m, w, g, s))) return rc;
             g = mk(w.mlp, lw[i].w_proj, lw[i].b_proj, w.x, w.x, rows, W, 4 * W, EPI_BIAS_RESID);
             g.stats_out = w.st1;
-            if ((rc = timed_gemm(m, g, s))) return rc;
+            if ((rc = timed_gemm(m, w, g, s))) return rc;
         }
         return CB_OK;
     }
@@ -291,14 +293,14 @@ int run_blocks(cb_clip *m, Ws &w, const LayerW *lw, int W, int heads, int B, int
         int rc;
         if (!(skip & 1))
         if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.h, lw[i].ln1_g, lw[i].ln1_b, rows, W, 1, nullptr, nullptr, 0, s); }))) return rc;
-        if ((rc = timed_gemm(m, mk(w.h, lw[i].w_qkv, lw[i].b_qkv, nullptr, w.qkv, rows, 3 * W, W, EPI_BIAS), s))) return rc;
+        if ((rc = timed_gemm(m, w, mk(w.h, lw[i].w_qkv, lw[i].b_qkv, nullptr, w.qkv, rows, 3 * W, W, EPI_BIAS), s))) return rc;
         if (!(skip & 2))
         if ((rc = timed_other(m, 1, s, [&] { return attention_f16(w.qkv, w.att, B, L, heads, causal, s); }))) return rc;
-        if ((rc = timed_gemm(m, mk(w.att, lw[i].w_o, lw[i].b_o, w.x, w.x, rows, W, W, EPI_BIAS_RESID), s))) return rc;
+        if ((rc = timed_gemm(m, w, mk(w.att, lw[i].w_o, lw[i].b_o, w.x, w.x, rows, W, W, EPI_BIAS_RESID), s))) return rc;
         if (!(skip & 1))
         if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.h, lw[i].ln2_g, lw[i].ln2_b, rows, W, 1, nullptr, nullptr, 0, s); }))) return rc;
-        if ((rc = timed_gemm(m, mk(w.h, lw[i].w_fc, lw[i].b_fc, nullptr, w.mlp, rows, 4 * W, W, EPI_BIAS_GELU), s))) return rc;
-        if ((rc = timed_gemm(m, mk(w.mlp, lw[i].w_proj, lw[i].b_proj, w.x, w.x, rows, W, 4 * W, EPI_BIAS_RESID), s))) return rc;
+        if ((rc = timed_gemm(m, w, mk(w.h, lw[i].w_fc, lw[i].b_fc, nullptr, w.mlp, rows, 4 * W, W, EPI_BIAS_GELU), s))) return rc;
+        if ((rc = timed_gemm(m, w, mk(w.mlp, lw[i].w_proj, lw[i].b_proj, w.x, w.x, rows, W, 4 * W, EPI_BIAS_RESID), s))) return rc;
     }
     return CB_OK;
 }
@@ -317,11 +319,12 @@ cudaError_t alloc_ws(const cb_clip *m, Ws &w) {
     A((void **)&w.cls, n_cls * 2); A((void **)&w.emb, nb * ED * 4); A((void **)&w.eot, nb * 4);
     const size_t rows = std::max(rows_v, rows_t);
     A((void **)&w.st1, rows * kMaxStatSlices * 8); A((void **)&w.st2, rows * kMaxStatSlices * 8);
+    A((void **)&w.skinny, kSkinnyScratchFloats * 4);
     return e;
 }
 
 void free_ws(Ws &w) {
-    void *bufs[] = {w.patches, w.x, w.h, w.qkv, w.att, w.mlp, w.cls, w.emb, w.eot, w.st1, w.st2};
+    void *bufs[] = {w.patches, w.x, w.h, w.qkv, w.att, w.mlp, w.cls, w.emb, w.eot, w.st1, w.st2, w.skinny};
     for (void *p : bufs) cudaFree(p);
     w = Ws();
 }
@@ -331,14 +334,14 @@ int vision_from_patches(cb_clip *m, Ws &w, int B, float *out_dev, int normalize,
     int rc;
     GemmArgs g = mk(w.patches, m->conv1_w, nullptr, nullptr, w.x, B * 49, VW, 3072, EPI_PATCH);
     g.pos = m->vpos;
-    if ((rc = timed_gemm(m, g, s))) return rc;
+    if ((rc = timed_gemm(m, w, g, s))) return rc;
     // ln_pre in place; class-token rows (row % 50 == 0) come from class_embedding + pos[0]
     if ((rc = timed_other(m, 2, s, [&] { return layernorm_f16(w.x, w.x, m->ln_pre_g, m->ln_pre_b, B * VL, VW, 1, nullptr, m->cls_pos, VL, s,
                                                                   m->ln_fold ? w.st1 : nullptr); }))) return rc;
     if ((rc = run_blocks(m, w, m->vis, VW, VH, B, VL, false, s))) return rc;
     if ((rc = layernorm_f16(w.x, w.cls, m->ln_post_g, m->ln_post_b, B, VW, VL, nullptr, nullptr, 0, s))) return rc;
     float *emb = normalize ? w.emb : out_dev;
-    if ((rc = timed_gemm(m, mk(w.cls, m->vproj_w, nullptr, nullptr, emb, B, ED, VW, EPI_F32), s))) return rc;
+    if ((rc = timed_gemm(m, w, mk(w.cls, m->vproj_w, nullptr, nullptr, emb, B, ED, VW, EPI_F32), s))) return rc;
     if (normalize && (rc = l2norm_rows_f32(emb, out_dev, B, ED, s))) return rc;
     return CB_OK;
 }
@@ -356,7 +359,7 @@ int text_forward(cb_clip *m, Ws &w, int B, const int32_t *ids_dev, float *out_de
     // ln_final only on the EOT rows (LayerNorm is per-row, so gathering first is exact)
     if ((rc = layernorm_f16(w.x, w.cls, m->lnf_g, m->lnf_b, B, TW, 1, w.eot, nullptr, 0, s))) return rc;
     float *emb = normalize ? w.emb : out_dev;
-    if ((rc = timed_gemm(m, mk(w.cls, m->tproj_w, nullptr, nullptr, emb, B, ED, TW, EPI_F32), s))) return rc;
+    if ((rc = timed_gemm(m, w, mk(w.cls, m->tproj_w, nullptr, nullptr, emb, B, ED, TW, EPI_F32), s))) return rc;
     if (normalize && (rc = l2norm_rows_f32(emb, out_dev, B, ED, s))) return rc;
     return CB_OK;
 }

@@ -30,6 +30,7 @@ enum Tune : int {
     T_GEMM_DEBUG,         // CLIPB200_GEMM_DEBUG         (only in -DCLIPB200_EXPERIMENTS builds) result-corrupting probes
     T_SKIP,               // CLIPB200_SKIP               (only in -DCLIPB200_EXPERIMENTS builds)
     T_PDL,                // CLIPB200_PDL                0: no programmatic dependent launch between the towers' kernels
+    T_GEMM_SKINNY,        // CLIPB200_GEMM_SKINNY        0: single-row-block GEMMs (M <= 128) use the general kernel; n > 0: force split n
     T_COUNT
 };
 int64_t tune(Tune t);

@@ -465,6 +465,243 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// ---- single-row-block GEMMs (M <= 128): a lean kernel, optionally split-K over a thread-block cluster ----
+// A single query (50 / 77 rows) makes every tower GEMM a read of the weight matrix with one 128-row tile of
+// A: one 128 x 64 output tile per CTA, 192 threads, a ring only as deep as the k-loop, operands of the
+// epilogue prefetched while the MMAs run, direct row stores.  With a cluster of S CTAs per tile, CTA r
+// multiplies k-blocks [r KB/S, (r+1) KB/S), parks its fp32 partial tile in a scratch buffer (L2), the cluster
+// synchronises (release / acquire at cluster scope) and the leader adds the S partials IN RANK ORDER
+// (deterministic) and runs the epilogue -- built, tested, and measured SLOWER than S = 1 (skinny_split below).
+constexpr int kSkinnyThreads = 192;     // warp 0 TMA, warp 1 TMEM + MMA, warps 2..5 epilogue (one TMEM lane quadrant each)
+constexpr int kSkinnyBN = 64;
+constexpr int kSkinnyStageBytes = BM * BK * 2 + kSkinnyBN * BK * 2;     // A 16 KB + W 8 KB
+constexpr int kSkinnyMaxStages = 6;
+__host__ __device__ constexpr int skinny_smem(int stages) { return stages * kSkinnyStageBytes + 256 + 1024 + 2 * kSkinnyBN * 4; }
+
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kSkinnyThreads, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
+                   const int kb_per_cta, const int num_stages) {
+    // the ring is as deep as this CTA's share of K (at most 6 stages): with a split of 4 or 8 that is 24 - 72 KB,
+    // so two or more CTAs share an SM and every cluster of the launch is resident at once
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + num_stages * kSkinnyStageBytes);
+    uint64_t *empty = full + kSkinnyMaxStages;
+    uint64_t *tfull = empty + kSkinnyMaxStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfull + 1);
+    float *s_bias = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(full) + 256);     // [64] bias, [64] colsum
+    float *s_csum = s_bias + kSkinnyBN;
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t S = cluster_nctarank(), crank = cluster_ctarank();
+    const int n_blk = blockIdx.x / S;
+    const int kb0 = (int)crank * kb_per_cta;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < num_stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+            mbar_init(tfull, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<1>(tmem_slot, 64);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+    pdl_launch_dependents();
+    pdl_wait();
+    if (g.stamp != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(g.stamp, t);
+    }
+
+    if (warp == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int i = 0; i < kb_per_cta; i++) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t *sa = smem + stage * kSkinnyStageBytes;
+            if (elect_one()) {
+                mbar_expect_tx(&full[stage], kSkinnyStageBytes);
+                tma_load_2d(sa, &tmA, (kb0 + i) * BK, 0, &full[stage]);
+                tma_load_2d(sa + BM * BK * 2, &tmB, (kb0 + i) * BK, n_blk * kSkinnyBN, &full[stage]);
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, kSkinnyBN);
+        uint32_t stage = 0, phase = 0;
+        for (int i = 0; i < kb_per_cta; i++) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kSkinnyStageBytes);
+            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + BM * BK * 2);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++) umma_f16<1>(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                umma_commit<1>(&empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit<1>(tfull);
+        __syncwarp();
+    }
+
+    // accumulator -> registers: thread = one row of the 128 x 64 tile
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool row_ok = row < g.M;
+    const int n0 = n_blk * kSkinnyBN;
+    constexpr bool kHasBias = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID;
+    const bool ln_fold = kHasBias && g.ln_stats != nullptr;
+    float acc[kSkinnyBN];
+    float ln_rstd = 1.f, ln_nrm = 0.f;
+    uint4 resid_row[EPI == EPI_BIAS_RESID ? kSkinnyBN / 8 : 1];
+    if (warp >= 2 && crank == 0) {
+        // the leader's epilogue operands do not depend on the MMAs: fetch them while the tensor core works
+        const int t = threadIdx.x - 64;
+        if (t < kSkinnyBN) {
+            s_bias[t] = (kHasBias && g.bias) ? __ldg(g.bias + n0 + t) : 0.f;
+            s_csum[t] = ln_fold ? __ldg(g.colsum + n0 + t) : 0.f;
+        }
+        if (ln_fold && row_ok) {
+            const float2 *sp = reinterpret_cast<const float2 *>(g.ln_stats) + (size_t)row * g.ln_slices;
+            float sx = 0.f, sxx = 0.f;
+            for (int i = 0; i < g.ln_slices; i++) { float2 p2 = __ldcg(sp + i); sx += p2.x; sxx += p2.y; }
+            const float inv = 1.0f / (float)g.K;
+            const float mean = sx * inv;
+            ln_rstd = rsqrtf(fmaxf(sxx * inv - mean * mean, 0.f) + 1e-5f);
+            ln_nrm = -ln_rstd * mean;
+        }
+        if (EPI == EPI_BIAS_RESID && row_ok) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(g.resid + (size_t)row * g.N + n0);
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN / 8; j++) resid_row[j] = rp[j];
+        }
+    }
+    if (warp >= 2) {
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[c * 32 + j] = __uint_as_float(v[j]);
+        }
+        if (S > 1 && row_ok) {
+            float4 *dst = reinterpret_cast<float4 *>(g.skinny_scratch + ((size_t)blockIdx.x * BM + row) * kSkinnyBN);
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN / 4; j++) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+    }
+    tc_fence_before();
+    if (S > 1) cluster_sync_all();           // every CTA's partial tile is visible to the leader
+    else __syncthreads();
+
+    if (warp >= 2 && crank == 0 && row_ok) {
+        if (S > 1) {
+            // partials in rank order: the sum does not depend on which CTA finished first
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN; j++) acc[j] = 0.f;
+            for (uint32_t r = 0; r < S; r++) {
+                const float4 *src = reinterpret_cast<const float4 *>(g.skinny_scratch + ((size_t)(blockIdx.x + r) * BM + row) * kSkinnyBN);
+#pragma unroll
+                for (int j = 0; j < kSkinnyBN / 4; j++) {
+                    const float4 f = __ldcg(src + j);
+                    acc[4 * j] += f.x; acc[4 * j + 1] += f.y; acc[4 * j + 2] += f.z; acc[4 * j + 3] += f.w;
+                }
+            }
+        }
+        if (ln_fold) {
+            // y = rstd * (acc - mean * colsum[n]) + b'[n]
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN; j++) acc[j] = fmaf(ln_rstd, acc[j], fmaf(ln_nrm, s_csum[j], s_bias[j]));
+        } else if (kHasBias) {
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN; j++) acc[j] += s_bias[j];
+        } else if (EPI == EPI_PATCH) {
+            const float *pos_row = g.pos + (size_t)(1 + row % 49) * g.N + n0;
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN; j++) acc[j] += __ldg(pos_row + j);
+        }
+        if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN; j++) {
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * acc[j]));
+                const float hx = 0.5f * acc[j];
+                acc[j] = fmaf(hx, t, hx);
+            }
+        }
+        if (EPI == EPI_BIAS_RESID) {
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN / 8; j++) {
+                const uint4 u = resid_row[j];
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float2 f = __half22float2(h[e]);
+                    acc[8 * j + 2 * e] += f.x;
+                    acc[8 * j + 2 * e + 1] += f.y;
+                }
+            }
+            if (g.stats_out != nullptr) {
+                // the folded LayerNorm of the next GEMM: (sum, sum of squares) per 32-column slice, as the
+                // general kernel's 64-wide tile writes them (gemm_out_slices)
+                const int out_slices = g.N / 32;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    float st_sum = 0.f, st_sq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) { st_sum += acc[c * 32 + j]; st_sq = fmaf(acc[c * 32 + j], acc[c * 32 + j], st_sq); }
+                    reinterpret_cast<float2 *>(g.stats_out)[(size_t)row * out_slices + n0 / 32 + c] = make_float2(st_sum, st_sq);
+                }
+            }
+        }
+        if (EPI == EPI_F32) {
+            float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.C) + (size_t)row * g.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN / 4; j++) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        } else {
+            const size_t orow = EPI == EPI_PATCH ? (size_t)(row + row / 49 + 1) : (size_t)row;
+            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(g.C) + orow * g.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < kSkinnyBN / 8; j++)
+                dst[j] = make_uint4(pack_h2(acc[8 * j], acc[8 * j + 1]), pack_h2(acc[8 * j + 2], acc[8 * j + 3]),
+                                    pack_h2(acc[8 * j + 4], acc[8 * j + 5]), pack_h2(acc[8 * j + 6], acc[8 * j + 7]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc<1>(tmem_base, 64);
+    }
+    if (g.stamp != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(g.stamp + 1, t);
+    }
+}
+
 // ---- host ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -568,6 +805,59 @@ int dispatch_epi(const GemmArgs &g, cudaStream_t s) {
     return CB_ERR_INVALID;
 }
 
+
+template <int EPI>
+int launch_skinny(const GemmArgs &g, int split, cudaStream_t s) {
+    auto kern = gemm_skinny_kernel<EPI>;
+    int cur_dev = 0;
+    CB_CUDA(cudaGetDevice(&cur_dev));
+    static std::once_flag attr_once[64];
+    cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once[cur_dev & 63], [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, skinny_smem(kSkinnyMaxStages));
+    });
+    CB_CUDA(attr_err);
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
+    if (rc) return rc;
+    if ((rc = make_map(&tmB, g.W, (uint64_t)g.N, (uint64_t)g.K, kSkinnyBN))) return rc;
+    const int n_tiles = g.N / kSkinnyBN, kb_per_cta = g.K / BK / split;
+    const int stages = std::min(kb_per_cta, kSkinnyMaxStages);
+    CB_CUDA(launch_ex(kern, dim3(n_tiles * split), dim3(kSkinnyThreads), skinny_smem(stages), s, split, true, tmA, tmB, g,
+                      kb_per_cta, stages));
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// Split factor of a single-row-block GEMM.  MEASURED NEGATIVE RESULT (profiles/r02_latency_skinny_sweep.txt):
+// single-query encode_image takes 0.476 ms with split 1, 0.529 / 0.585 / 0.601 ms with split 2 / 4 / 8 (general
+// kernel: 0.487 ms).  The ~7 us per launch of a single-query forward pass is launch + prologue + one HBM round
+// trip + epilogue, not the serial walk over K: the cluster barrier and the scratch round trip cost more than the
+// shorter k-loop saves.  The default is therefore NO split; the knob gemm_skinny = 2 / 4 / 8 forces one (tests).
+int skinny_split(const GemmArgs &g, int sms) {
+    (void)sms;
+    if (g.skinny_scratch == nullptr) return 1;
+    const int n_tiles = g.N / kSkinnyBN, kb = g.K / BK;
+    if (tune(T_GEMM_SKINNY) > 0) {
+        const int f = (int)tune(T_GEMM_SKINNY);
+        if ((f == 1 || f == 2 || f == 4 || f == 8) && kb % f == 0 && (size_t)n_tiles * f * BM * kSkinnyBN <= kSkinnyScratchFloats) return f;
+    }
+    return 1;
+}
+
+int dispatch_skinny(const GemmArgs &g, int sms, cudaStream_t s) {
+    const int split = skinny_split(g, sms);
+    switch (g.epilogue) {
+        case EPI_BIAS: return launch_skinny<EPI_BIAS>(g, split, s);
+        case EPI_BIAS_GELU: return launch_skinny<EPI_BIAS_GELU>(g, split, s);
+        case EPI_BIAS_RESID: return launch_skinny<EPI_BIAS_RESID>(g, split, s);
+        case EPI_PATCH: return launch_skinny<EPI_PATCH>(g, split, s);
+        case EPI_F32: return launch_skinny<EPI_F32>(g, split, s);
+    }
+    set_error("gemm_f16: unknown epilogue %d", g.epilogue);
+    return CB_ERR_INVALID;
+}
+
 // Pick cluster size and N tile.  A CTA pair is used whenever the problem has more than one
 // 128-row block (it halves the W traffic per SM and measured faster on every tower shape,
 // profiles/r01_gemm_sweep.txt); the N tile is the one that minimises
@@ -624,6 +914,10 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int ncta = 1, bn = 128;
     pick_config(g.M, g.N, sms, &ncta, &bn);
+    // one row block: the split-K cluster kernel (same 64-wide tile, same statistics layout as the general kernel)
+    if (g.M <= BM && g.N % kSkinnyBN == 0 && tune(T_GEMM_SKINNY) != 0 && tune(T_GEMM_BN) <= 0 && tune(T_GEMM_NCTA) <= 0 &&
+        ((uintptr_t)g.C & 15) == 0 && (g.ldc % 8) == 0)
+        return dispatch_skinny(g, sms, stream);
     if (!g.stats_out) {      // test/experiment overrides (the stats layout depends on the default choice)
         if (tune(T_GEMM_BN) > 0) {
             int v = (int)tune(T_GEMM_BN);
@@ -654,6 +948,18 @@ int gemm_f16(const GemmArgs &g, cudaStream_t stream) {
 
 }  // namespace cb
 
+// the stand-alone entry points own no workspace: a single-row-block GEMM borrows its split-K scratch from the
+// stream-ordered allocator for the duration of the launch
+static int gemm_with_scratch(cb::GemmArgs &g, cudaStream_t s) {
+    if (g.M > 128) return cb::gemm_f16(g, s);
+    float *scratch = nullptr;
+    CB_CUDA(cudaMallocAsync(&scratch, cb::kSkinnyScratchFloats * sizeof(float), s));
+    g.skinny_scratch = scratch;
+    const int rc = cb::gemm_f16(g, s);
+    CB_CUDA(cudaFreeAsync(scratch, s));
+    return rc;
+}
+
 extern "C" int cb_gemm_f16_ex_device(int M, int N, int K, const void *A, const void *W, const float *bias,
                                      const void *resid, void *C, int epilogue, const float *ln_stats, int ln_slices,
                                      const float *colsum, float *stats_out, void *stream) {
@@ -661,7 +967,7 @@ extern "C" int cb_gemm_f16_ex_device(int M, int N, int K, const void *A, const v
     g.A = (const __half *)A; g.W = (const __half *)W; g.bias = bias; g.resid = (const __half *)resid;
     g.pos = nullptr; g.C = C; g.M = M; g.N = N; g.K = K; g.ldc = N; g.epilogue = epilogue;
     g.ln_stats = ln_stats; g.ln_slices = ln_slices; g.colsum = colsum; g.stats_out = stats_out;
-    return cb::gemm_f16(g, (cudaStream_t)stream);
+    return gemm_with_scratch(g, (cudaStream_t)stream);
 }
 
 extern "C" int cb_gemm_out_slices(int M, int N) { return cb::gemm_out_slices(M, N); }
@@ -672,5 +978,5 @@ extern "C" int cb_gemm_f16_device(int M, int N, int K, const void *A, const void
     cb::GemmArgs g;
     g.A = (const __half *)A; g.W = (const __half *)W; g.bias = bias; g.resid = (const __half *)resid;
     g.pos = pos; g.C = C; g.M = M; g.N = N; g.K = K; g.ldc = ldc > 0 ? ldc : N; g.epilogue = epilogue;
-    return cb::gemm_f16(g, (cudaStream_t)stream);
+    return gemm_with_scratch(g, (cudaStream_t)stream);
 }

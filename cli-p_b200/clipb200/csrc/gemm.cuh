@@ -43,7 +43,13 @@ struct GemmArgs {
     // kernel entry) and stamp[1] (max at exit), so the launch's duration is measured on the device
     // without host-side event gaps.  Null in the product path.
     unsigned long long *stamp = nullptr;
+    // fp32 scratch for the split-K form of single-row-block GEMMs (M <= 128): kSkinnyScratchFloats floats,
+    // private to the stream the GEMM runs on.  Null: no split (each CTA walks all of K).
+    float *skinny_scratch = nullptr;
 };
+
+// scratch size for GemmArgs::skinny_scratch: (N / 64) n-tiles x split factor <= 148 CTAs, 128 x 64 floats each
+constexpr size_t kSkinnyScratchFloats = (size_t)148 * 128 * 64;
 
 // returns a CB_* code; launches on `stream`
 int gemm_f16(const GemmArgs &g, cudaStream_t stream);

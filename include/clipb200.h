@@ -50,6 +50,8 @@ int cb_device_count(int *n);
  *   ln_blocks_per_sm   LayerNorm grid size
  *   ln_fold            0 / 1 / unset: see cb_clip_finalize
  *   pdl                0: the towers' kernels are launched without programmatic dependent launch
+ *   gemm_skinny        0: single-row-block GEMMs (M <= 128) use the general kernel; 2 / 4 / 8: force a
+ *                      cluster split-K of that factor (measured slower than no split; kept for tests)
  * Result-corrupting perf probes (gemm_debug, skip) exist only in -DCLIPB200_EXPERIMENTS builds. */
 int cb_tuning_set(const char *name, int64_t value);
 int cb_tuning_get(const char *name, int64_t *value);

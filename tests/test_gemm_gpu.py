@@ -176,3 +176,48 @@ def test_layernorm_folded_into_gemm(M, W, epi, outlier):
         ref = ref * torch.sigmoid(1.702 * ref)
     err = (y.float() - ref).abs()
     assert err.max().item() <= 3e-2 and err.mean().item() <= 3e-3, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize("split", [-1, 1, 2, 4, 8])
+@pytest.mark.parametrize("M,N,K,epi", [(50, 2304, 768, EPI_BIAS), (77, 2048, 512, EPI_BIAS_GELU), (1, 768, 3072, EPI_BIAS_RESID),
+                                       (128, 512, 2048, EPI_BIAS_RESID), (98, 768, 3072, EPI_PATCH), (3, 512, 768, EPI_F32)])
+def test_single_row_block_split_k(M, N, K, epi, split):
+    """M <= 128 (a single query): the cluster split-K kernel, every epilogue, every split factor (split = -1:
+    the library's own choice): against fp32 torch, bit-identical across repeated launches (partials are
+    summed in rank order), and within fp16 rounding of the general kernel (gemm_skinny = 0)."""
+    import torch
+    from clipb200 import _native
+    g = torch.Generator(device="cuda").manual_seed(M * 31 + N + K + epi)
+    A = (torch.randn((M, K), generator=g, device="cuda") * 0.5).half()
+    W = (torch.randn((N, K), generator=g, device="cuda") * K ** -0.5).half()
+    b = torch.randn((N,), generator=g, device="cuda") if epi in (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID) else None
+    pos = torch.randn((50, N), generator=g, device="cuda") if epi == EPI_PATCH else None
+    x0 = torch.randn((M, N), generator=g, device="cuda").half() if epi == EPI_BIAS_RESID else None
+    rows = M + M // 49 + 1 if epi == EPI_PATCH else M
+
+    def run():
+        out = torch.zeros((rows, N), dtype=torch.float32 if epi == EPI_F32 else torch.float16, device="cuda")
+        x = x0.clone() if x0 is not None else None
+        return _gemm(torch, A, W, bias=b, resid=x, pos=pos, epi=epi, out=x if x is not None else out)
+
+    acc = A.float() @ W.float().T
+    if epi in (EPI_BIAS, EPI_BIAS_GELU):
+        ref = acc + b
+        if epi == EPI_BIAS_GELU:
+            ref = ref * torch.sigmoid(1.702 * ref)
+    elif epi == EPI_BIAS_RESID:
+        ref = acc + b + x0.float()
+    elif epi == EPI_PATCH:
+        ref = torch.zeros((rows, N), device="cuda")
+        r = torch.arange(M, device="cuda")
+        ref[r + r // 49 + 1] = acc + pos[1 + r % 49]
+    else:
+        ref = acc
+    with _native.tuning(gemm_skinny=split):
+        got = run()
+        again = run()
+    assert torch.equal(got, again), "split-K result depends on the order the CTAs finished"
+    _close(torch, got, ref, tol=4e-3 if epi == EPI_BIAS_GELU else (1e-4 if epi == EPI_F32 else 2e-3))
+    with _native.tuning(gemm_skinny=0):
+        general = run()
+    assert (got.float() - general.float()).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
