@@ -112,7 +112,8 @@ cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
     }
     if (pdl && tune(T_PDL) != 0) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
+        if (tune(T_PDL) != 2 &&          // pdl = 2: keep the attribute inside CUDA-graph captures as well
+            cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
         if (cs == cudaStreamCaptureStatusNone) {
             attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[na].val.programmaticStreamSerializationAllowed = 1;

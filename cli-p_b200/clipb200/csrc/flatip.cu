@@ -717,9 +717,9 @@ namespace {
 // kSlots x world result slots of `cap` elements each (D block fp32, then I block int64).
 constexpr int kSlots = 2;                 // a rank may run one search ahead of the root's merge
 constexpr size_t kMailHeader = 256;
-constexpr size_t kOffDone = 0;            // uint32 done[kMaxRanks]
-constexpr size_t kOffConsumed = 64;       // uint32 consumed
-constexpr size_t kOffError = 68;          // uint32 error
+constexpr size_t kOffDone = 0;            // uint32 done[kSlots][kMaxRanks]: queries delivered into a slot, per rank
+constexpr size_t kOffConsumed = 128;      // uint32 consumed[kSlots]: queries of a slot merged by the root
+constexpr size_t kOffError = 192;         // uint32 error
 
 struct P2P {
     bool attached = false;
@@ -728,15 +728,15 @@ struct P2P {
     char *own = nullptr;                  // allocation owned by this index (rank 0 only)
     char *root = nullptr;                 // the root's mailbox as addressable from this device
     bool root_is_ipc = false;             // opened with cudaIpcOpenMemHandle (close on free)
-    uint32_t seq = 0;                     // searches issued so far
-    uint32_t total = 0;                   // queries issued so far (cumulative, wraps)
-    uint32_t ring[kSlots] = {0};          // `total` after the search that last used each slot
+    uint32_t seq = 0;                     // searches issued so far (slot = seq % kSlots = the search lane)
+    uint32_t ring[kSlots] = {0};          // queries issued into each slot so far (cumulative, wraps)
     // root only: merge scratch for very large k
     size_t slot_bytes() const { return (size_t)cap * 12; }
     float *slot_D(int slot, int r) const { return reinterpret_cast<float *>(root + kMailHeader + ((size_t)slot * world + r) * slot_bytes()); }
     int64_t *slot_I(int slot, int r) const { return reinterpret_cast<int64_t *>(reinterpret_cast<char *>(slot_D(slot, r)) + (size_t)cap * 4); }
-    uint32_t *done() const { return reinterpret_cast<uint32_t *>(root + kOffDone); }
-    uint32_t *consumed() const { return reinterpret_cast<uint32_t *>(root + kOffConsumed); }
+    // counters are per slot: the two slots belong to two search lanes whose kernels may finish out of order
+    uint32_t *done(int slot) const { return reinterpret_cast<uint32_t *>(root + kOffDone) + slot * kMaxRanks; }
+    uint32_t *consumed(int slot) const { return reinterpret_cast<uint32_t *>(root + kOffConsumed) + slot; }
     uint32_t *error() const { return reinterpret_cast<uint32_t *>(root + kOffError); }
     size_t bytes() const { return kMailHeader + (size_t)kSlots * world * slot_bytes(); }
 };
@@ -753,13 +753,23 @@ struct cb_index {
     cudaStream_t stream = nullptr;   // used by the host-pointer entry points
     cudaEvent_t add_ev = nullptr;    // orders ix->stream after add_device() calls on foreign streams
     float *max_norm2 = nullptr;      // device scalar: max ||row||^2 over the shard (as stored)
-    // search workspace
-    float *scores = nullptr;         // [kMaxNQ][score_stride]
-    int64_t score_stride = 0;
-    QueryWs *ws = nullptr;           // [kMaxNQ]; zero between searches (the collect kernel re-zeroes it)
-    bool ws_dirty = true;
-    uint64_t *cand = nullptr;        // [kMaxNQ][cand_cap]
-    uint32_t cand_cap = 0;
+    // search workspace: two lanes.  The plain entry points use lane 0 on the caller's stream; the pipelined
+    // submit / join pair alternates lanes (own stream + workspace each), so the selection + exchange tail of
+    // one query overlaps the pass over the shard of the next.
+    struct Lane {
+        float *scores = nullptr;         // [kMaxNQ][score_stride]
+        int64_t score_stride = 0;
+        QueryWs *ws = nullptr;           // [kMaxNQ]; zero between searches (the search kernel re-zeroes it)
+        bool ws_dirty = true;
+        uint64_t *cand = nullptr;        // [kMaxNQ][cand_cap]
+        uint32_t cand_cap = 0;
+        cb::BatchWs *bws = nullptr;      // workspace of the tensor-core batch path
+        cudaStream_t stream = nullptr;   // lane stream of the submit API
+        cudaEvent_t done = nullptr, fence = nullptr;
+        bool used = false;
+    } lanes[2];
+    int next_lane = 0;
+    bool half_grid = false;          // submit API: two searches in flight share the SMs
     // global-id segments of a shard inside a multi-shard index (cb_sharded): device copies
     int64_t *seg_dev = nullptr;      // [2][seg_cap]: local starts, then global starts
     int seg_cap = 0, nseg = 0;
@@ -773,7 +783,6 @@ struct cb_index {
     int64_t stage_bytes = 0;
     int scan_blocks_per_sm[2][3] = {{0}};
     int sms = 0;
-    cb::BatchWs *bws = nullptr;      // workspace of the tensor-core batch path
     int64_t n_batch_searches = 0;
     P2P p2p;
     // optional live timing of the scan kernel (bench.py roofline): event pairs on the
@@ -811,35 +820,35 @@ static int grow_rows(cb_index *ix, int64_t need, cudaStream_t s) {
     return CB_OK;
 }
 
-static int ensure_ws(cb_index *ix, int64_t k_eff) {
+static int ensure_ws(cb_index *ix, cb_index::Lane &L, int64_t k_eff) {
     const int64_t stride = (ix->ntotal + 63) / 64 * 64;
-    if (stride > ix->score_stride) {
-        if (ix->scores) CB_CUDA(cudaFree(ix->scores));
-        ix->scores = nullptr;
+    if (stride > L.score_stride) {
+        if (L.scores) CB_CUDA(cudaFree(L.scores));
+        L.scores = nullptr;
         int64_t s = std::max<int64_t>(stride, (ix->capacity + 63) / 64 * 64);
-        CB_CUDA(cudaMalloc(&ix->scores, (size_t)kMaxNQ * s * sizeof(float)));
-        ix->score_stride = s;
+        CB_CUDA(cudaMalloc(&L.scores, (size_t)kMaxNQ * s * sizeof(float)));
+        L.score_stride = s;
     }
-    if (!ix->ws) {
-        CB_CUDA(cudaMalloc(&ix->ws, sizeof(QueryWs) * kMaxNQ));
-        ix->ws_dirty = true;
+    if (!L.ws) {
+        CB_CUDA(cudaMalloc(&L.ws, sizeof(QueryWs) * kMaxNQ));
+        L.ws_dirty = true;
     }
     // room for the short list (everything in the bins at or above the k-th score's bin: k plus a bin's worth
     // of rows) as long as it can still be sorted in shared memory; never less than k
     uint32_t p2 = 256;
     while ((int64_t)p2 < std::min<int64_t>(2 * k_eff, kSortSmem) || (int64_t)p2 < k_eff) p2 <<= 1;
-    if (p2 > ix->cand_cap) {
-        if (ix->cand) CB_CUDA(cudaFree(ix->cand));
-        ix->cand = nullptr;
-        CB_CUDA(cudaMalloc(&ix->cand, (size_t)kMaxNQ * p2 * sizeof(uint64_t)));
-        ix->cand_cap = p2;
+    if (p2 > L.cand_cap) {
+        if (L.cand) CB_CUDA(cudaFree(L.cand));
+        L.cand = nullptr;
+        CB_CUDA(cudaMalloc(&L.cand, (size_t)kMaxNQ * p2 * sizeof(uint64_t)));
+        L.cand_cap = p2;
     }
     return CB_OK;
 }
 
 template <int NQ, bool F16>
-static int launch_search(cb_index *ix, const float *q_dev, int nq_valid, uint32_t k_eff, int64_t k, float *D_dev,
-                         int64_t *I_dev, const IdMap &ids, const PeerOut &po, cudaStream_t s) {
+static int launch_search(cb_index *ix, cb_index::Lane &L, const float *q_dev, int nq_valid, uint32_t k_eff, int64_t k,
+                         float *D_dev, int64_t *I_dev, const IdMap &ids, const PeerOut &po, cudaStream_t s) {
     auto kern = flatip_search_kernel<NQ, F16>;
     // phase 1 histograms, later reused as the sort buffer of the last block
     const size_t smem = std::max<size_t>((size_t)NQ * kBins0 * sizeof(uint32_t), (size_t)kSortSmem * sizeof(uint64_t));
@@ -853,8 +862,10 @@ static int launch_search(cb_index *ix, const float *q_dev, int nq_valid, uint32_
     constexpr int R = F16 ? 8 : 4;
     int64_t groups = (ix->ntotal + R - 1) / R;
     int64_t want = (groups + (kScanThreads / 32) - 1) / (kScanThreads / 32);
-    // cooperative launch: every block is resident (the kernel has grid-wide barriers)
-    int grid = (int)std::min<int64_t>((int64_t)ix->sms * bps, std::max<int64_t>(want, 1));
+    // cooperative launch: every block is resident (the kernel has grid-wide barriers).  Two searches in flight
+    // (submit API) take half of the residency each, so that both are resident at once.
+    const int per_sm = ix->half_grid ? std::max(1, bps / 2) : bps;
+    int grid = (int)std::min<int64_t>((int64_t)ix->sms * per_sm, std::max<int64_t>(want, 1));
     const bool timed = ix->timing && ix->ev_n < cb_index::kEv;
     if (timed) {
         if (!ix->ev0[ix->ev_n]) {
@@ -864,11 +875,11 @@ static int launch_search(cb_index *ix, const float *q_dev, int nq_valid, uint32_
         CB_CUDA(cudaEventRecord(ix->ev0[ix->ev_n], s));
     }
     const uint4 *rows = (const uint4 *)ix->rows;
-    int64_t n = ix->ntotal, stride = ix->score_stride;
-    float *scores = ix->scores;
-    QueryWs *ws = ix->ws;
-    uint64_t *cand = ix->cand;
-    uint32_t cand_cap = ix->cand_cap;
+    int64_t n = ix->ntotal, stride = L.score_stride;
+    float *scores = L.scores;
+    QueryWs *ws = L.ws;
+    uint64_t *cand = L.cand;
+    uint32_t cand_cap = L.cand_cap;
     const float *mx = ix->max_norm2;
     IdMap ids_v = ids;
     PeerOut po_v = po;
@@ -892,24 +903,24 @@ static int launch_search(cb_index *ix, const float *q_dev, int nq_valid, uint32_
 }
 
 // the streaming path over <= kMaxNQ queries: ONE cooperative launch (scan + select + write)
-static int search_tile(cb_index *ix, int nq, const float *q_dev, int64_t k, float *D_dev,
+static int search_tile(cb_index *ix, cb_index::Lane &L, int nq, const float *q_dev, int64_t k, float *D_dev,
                        int64_t *I_dev, const IdMap &ids, const PeerOut &po, cudaStream_t s) {
     const int64_t n = ix->ntotal;
     const uint32_t k_eff = (uint32_t)std::min<int64_t>(k, n);
     // histograms + state are zero between searches: the kernel's last block re-zeroes them.  Only a search
     // that failed half way needs a memset.
-    if (ix->ws_dirty) CB_CUDA(cudaMemsetAsync(ix->ws, 0, sizeof(QueryWs) * kMaxNQ, s));
-    ix->ws_dirty = true;
+    if (L.ws_dirty) CB_CUDA(cudaMemsetAsync(L.ws, 0, sizeof(QueryWs) * kMaxNQ, s));
+    L.ws_dirty = true;
     const bool f16 = ix->dtype == CB_F16;
     int rc;
-    if (nq == 1) rc = f16 ? launch_search<1, true>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
-                          : launch_search<1, false>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
-    else if (nq == 2) rc = f16 ? launch_search<2, true>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
-                               : launch_search<2, false>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
-    else rc = f16 ? launch_search<4, true>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
-                  : launch_search<4, false>(ix, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
+    if (nq == 1) rc = f16 ? launch_search<1, true>(ix, L, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
+                          : launch_search<1, false>(ix, L, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
+    else if (nq == 2) rc = f16 ? launch_search<2, true>(ix, L, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
+                               : launch_search<2, false>(ix, L, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
+    else rc = f16 ? launch_search<4, true>(ix, L, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s)
+                  : launch_search<4, false>(ix, L, q_dev, nq, k_eff, k, D_dev, I_dev, ids, po, s);
     if (rc) return rc;
-    ix->ws_dirty = false;
+    L.ws_dirty = false;
     return CB_OK;
 }
 
@@ -918,7 +929,8 @@ static int search_tile(cb_index *ix, int nq, const float *q_dev, int64_t k, floa
 // tcgen05 GEMM with a fused per-query threshold filter and exact fp32 re-scoring (tensor-bound).
 // Nothing here synchronises.  With `po` set, every query's list is delivered to the root's mailbox.
 static int search_core(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev, int64_t *I_dev,
-                       const IdMap &ids, const PeerOut &po, cudaStream_t s) {
+                       const IdMap &ids, const PeerOut &po, cudaStream_t s, int lane = 0) {
+    cb_index::Lane &L = ix->lanes[lane];
     if (ix->ntotal == 0) {
         fill_empty_kernel<<<1, 256, 0, s>>>(D_dev, I_dev, nq * k, po, (uint32_t)nq);
         CB_LAUNCH_CHECK();
@@ -931,18 +943,18 @@ static int search_core(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, 
     int64_t batch_min = ix->ntotal >= (1ll << 20) ? 2 : 16;
     if (tune(T_BATCH_MIN_NQ) > 0) batch_min = tune(T_BATCH_MIN_NQ);
     if (nq >= batch_min && ix->dtype == CB_F16 && k <= 1024 && ix->ntotal >= 8192) {
-        if (!ix->bws) ix->bws = batch_ws_new();
-        int brc = flatip_search_batch(ix->bws, ix->rows, ix->ntotal, ix->device, nq, q_dev, k, D_dev, I_dev, ids, po,
+        if (!L.bws) L.bws = batch_ws_new();
+        int brc = flatip_search_batch(L.bws, ix->rows, ix->ntotal, ix->device, nq, q_dev, k, D_dev, I_dev, ids, po,
                                       ix->max_norm2, s);
         if (brc) return brc;
         ix->n_batch_searches++;
         return CB_OK;
     }
-    int rc = ensure_ws(ix, std::min<int64_t>(k, ix->ntotal));
+    int rc = ensure_ws(ix, L, std::min<int64_t>(k, ix->ntotal));
     if (rc) return rc;
     for (int64_t q0 = 0; q0 < nq; q0 += kMaxNQ) {
         int t = (int)std::min<int64_t>(kMaxNQ, nq - q0);
-        rc = search_tile(ix, t, q_dev + q0 * ix->d, k, D_dev + q0 * k, I_dev + q0 * k, ids, po, s);
+        rc = search_tile(ix, L, t, q_dev + q0 * ix->d, k, D_dev + q0 * k, I_dev + q0 * k, ids, po, s);
         if (rc) return rc;
     }
     return CB_OK;
@@ -1022,21 +1034,23 @@ static int p2p_alloc_root(cb_index *ix, int world, int64_t max_elems) {
 // The local part of a sharded search: this rank's top-k goes into the root's mailbox slot.
 // Returns the slot and the cumulative query count after this search.
 static int p2p_local_search(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, int64_t id_base, cudaStream_t s,
-                            int *slot_out, uint32_t *total_out) {
+                            int *slot_out, uint32_t *total_out, int lane = -1) {
     P2P &p = ix->p2p;
-    const int slot = (int)(p.seq % kSlots);
+    // slot = lane of the submit API; the plain entry points alternate slots on one stream (every rank issues
+    // the same sequence of calls, so every rank picks the same slot)
+    const int slot = lane >= 0 ? lane : (int)(p.seq % kSlots);
     PeerOut po;
-    po.done = p.done() + p.rank;
-    po.consumed = p.consumed();
+    po.done = p.done(slot) + p.rank;
+    po.consumed = p.consumed(slot);
     po.need_consumed = p.ring[slot];          // the search that last used this slot must be merged
     po.error = p.error();
-    int rc = search_core(ix, nq, q_dev, k, p.slot_D(slot, p.rank), p.slot_I(slot, p.rank), ix->idmap(id_base), po, s);
+    int rc = search_core(ix, nq, q_dev, k, p.slot_D(slot, p.rank), p.slot_I(slot, p.rank), ix->idmap(id_base), po, s,
+                         std::max(lane, 0));
     if (rc) return rc;
-    p.total += (uint32_t)nq;
-    p.ring[slot] = p.total;
+    p.ring[slot] += (uint32_t)nq;
     p.seq++;
     *slot_out = slot;
-    *total_out = p.total;
+    *total_out = p.ring[slot];
     return CB_OK;
 }
 
@@ -1044,9 +1058,9 @@ static int p2p_root_merge(cb_index *ix, int slot, uint32_t total, int64_t nq, in
                           cudaStream_t s) {
     P2P &p = ix->p2p;
     MergeSync ms;
-    ms.done = p.done();
+    ms.done = p.done(slot);
     ms.need_done = total;
-    ms.consumed = p.consumed();
+    ms.consumed = p.consumed(slot);
     ms.error = p.error();
     const int64_t stride_D = (int64_t)(p.slot_bytes() / 4), stride_I = (int64_t)(p.slot_bytes() / 8);
     return launch_merge(p.world, nq, k, p.slot_D(slot, 0), p.slot_I(slot, 0), stride_D, stride_I, D_dev, I_dev, ms, s);
@@ -1114,11 +1128,18 @@ void cb_flatip_free(cb_index *ix) {
     DeviceGuard g(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     p2p_detach(ix);
-    cudaFree(ix->rows); cudaFree(ix->scores); cudaFree(ix->ws); cudaFree(ix->cand);
+    cudaFree(ix->rows);
+    for (cb_index::Lane &L : ix->lanes) {
+        if (L.stream) cudaStreamSynchronize(L.stream);
+        cudaFree(L.scores); cudaFree(L.ws); cudaFree(L.cand);
+        cb::batch_ws_delete(L.bws);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.fence) cudaEventDestroy(L.fence);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
     cudaFree(ix->d_q); cudaFree(ix->d_D); cudaFree(ix->d_I); cudaFree(ix->d_stage);
     cudaFree(ix->max_norm2); cudaFree(ix->seg_dev); cudaFree(ix->phase_t);
     cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_D); cudaFreeHost(ix->h_I);
-    cb::batch_ws_delete(ix->bws);
     for (int i = 0; i < cb_index::kEv; i++) {
         if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
         if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]);
@@ -1336,6 +1357,56 @@ int cb_flatip_search_p2p_device(cb_index *ix, int64_t nq, const float *q_dev, in
     return CB_OK;
 }
 
+// Pipelined form: queue one search and return.  Searches alternate between two lanes (own stream, workspace
+// and mailbox slot); each lane's kernels take half of the SMs' residency, so the selection / exchange / merge
+// tail of one query overlaps the pass over the shard of the next.  Works with or without an attached mailbox.
+int cb_flatip_submit_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
+                                   int64_t *I_dev, int64_t id_base, void *after_stream) {
+    CB_REQUIRE(ix != nullptr, "cb_flatip_submit_search_device: null index");
+    CB_REQUIRE(nq > 0 && k > 0 && k < (1ll << 31), "cb_flatip_submit_search_device: nq and k must be > 0");
+    CB_REQUIRE(q_dev != nullptr, "cb_flatip_submit_search_device: null query");
+    P2P &p = ix->p2p;
+    const bool peer = p.attached && p.world > 1;
+    CB_REQUIRE((peer && p.rank != 0) || (D_dev && I_dev), "cb_flatip_submit_search_device: null output buffer");
+    CB_REQUIRE(!peer || nq * k <= p.cap, "cb_flatip_submit_search_device: nq * k = %lld exceeds a mailbox slot (%lld)",
+               (long long)(nq * k), (long long)p.cap);
+    DeviceGuard g(ix->device);
+    const int lane = ix->next_lane;
+    ix->next_lane ^= 1;
+    cb_index::Lane &L = ix->lanes[lane];
+    if (!L.stream) {
+        CB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CB_CUDA(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        CB_CUDA(cudaEventCreateWithFlags(&L.fence, cudaEventDisableTiming));
+    }
+    CB_CUDA(cudaEventRecord(L.fence, (cudaStream_t)after_stream));
+    CB_CUDA(cudaStreamWaitEvent(L.stream, L.fence, 0));
+    ix->half_grid = true;
+    int rc;
+    if (peer) {
+        int slot = 0;
+        uint32_t total = 0;
+        rc = p2p_local_search(ix, nq, q_dev, k, id_base, L.stream, &slot, &total, lane);
+        if (!rc && p.rank == 0) rc = p2p_root_merge(ix, slot, total, nq, k, D_dev, I_dev, L.stream);
+    } else {
+        rc = search_core(ix, nq, q_dev, k, D_dev, I_dev, ix->idmap(id_base), PeerOut(), L.stream, lane);
+    }
+    ix->half_grid = false;
+    if (rc) return rc;
+    CB_CUDA(cudaEventRecord(L.done, L.stream));
+    L.used = true;
+    return CB_OK;
+}
+
+// make `stream` wait for every submitted search (no host synchronisation)
+int cb_flatip_join(cb_index *ix, void *stream) {
+    CB_REQUIRE(ix != nullptr, "cb_flatip_join: null index");
+    DeviceGuard g(ix->device);
+    for (cb_index::Lane &L : ix->lanes)
+        if (L.used) CB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, L.done, 0));
+    return CB_OK;
+}
+
 int cb_flatip_p2p_status(cb_index *ix, int *error) {
     CB_REQUIRE(ix && error, "cb_flatip_p2p_status: null argument");
     *error = 0;
@@ -1351,10 +1422,14 @@ int cb_flatip_batch_stats(cb_index *ix, int64_t *n_batch_searches, int64_t *n_re
     CB_REQUIRE(ix && n_batch_searches && n_rescued, "cb_flatip_batch_stats: null argument");
     *n_batch_searches = ix->n_batch_searches;
     *n_rescued = 0;
-    if (ix->bws) {
-        DeviceGuard g(ix->device);
-        return batch_ws_stats(ix->bws, n_rescued, ix->stream);
-    }
+    DeviceGuard g(ix->device);
+    for (cb_index::Lane &L : ix->lanes)
+        if (L.bws) {
+            int64_t r = 0;
+            int rc = batch_ws_stats(L.bws, &r, ix->stream);
+            if (rc) return rc;
+            *n_rescued += r;
+        }
     return CB_OK;
 }
 

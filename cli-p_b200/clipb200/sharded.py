@@ -164,6 +164,32 @@ class DistributedFlatIP:
                                                     self.id_base, C.c_void_p(stream)))
         return D, I
 
+    # ---- pipelined query stream ---------------------------------------------------------------------
+    def submit(self, q: torch.Tensor, k: int, out=None):
+        """Queue one search and return at once (cb_flatip_submit_search_device): consecutive submissions
+        alternate between two lanes, so the selection / exchange / merge tail of one query overlaps the pass
+        over the shard of the next.  `out` = (D, I) tensors to fill (rank 0; allocated when omitted).  The
+        results are valid after join(); q and out must stay untouched until then."""
+        from . import _native as N
+        assert self.transport == "p2p" or self.world == 1, "submit() needs the p2p transport"
+        nq = q.shape[0]
+        D = I = None
+        dp = ip = None
+        if self.rank == 0:
+            D, I = out if out is not None else (torch.empty((nq, k), dtype=torch.float32, device=self.device),
+                                                torch.empty((nq, k), dtype=torch.int64, device=self.device))
+            dp, ip = C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr())
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        N.check(N.lib().cb_flatip_submit_search_device(self._handle(), nq, C.c_void_p(q.data_ptr()), k, dp, ip,
+                                                       self.id_base, C.c_void_p(stream)))
+        return D, I
+
+    def join(self) -> None:
+        """Order the current torch stream after every submitted search (no host synchronisation)."""
+        from . import _native as N
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(N.lib().cb_flatip_join(self._handle(), C.c_void_p(stream)))
+
     def _search_collective(self, q: torch.Tensor, k: int):
         nq = q.shape[0]
         off_I, total = self._buffers(nq, k)

@@ -130,6 +130,15 @@ int cb_flatip_p2p_connect(cb_index *ix, const void *root_ipc_handle64);
  * max_elems per mailbox slot; k <= max_elems. */
 int cb_flatip_search_p2p_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
                                 int64_t *I_dev, int64_t id_base, void *stream);
+/* Pipelined form for query streams: queue one search and return; results are ordered on a stream by
+ * cb_flatip_join.  Searches alternate between two lanes (own stream, workspace and mailbox slot) and each
+ * lane's kernels take half of the SMs' residency, so the selection / exchange / merge tail of one query
+ * overlaps the pass over the shard of the next.  With an attached mailbox every rank submits the same
+ * sequence and (D, I) are written on rank 0; without one it is the plain local search.  The query and
+ * output buffers of a submitted search must stay untouched until the join; nq * k <= max_elems. */
+int cb_flatip_submit_search_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
+                                   int64_t *I_dev, int64_t id_base, void *after_stream);
+int cb_flatip_join(cb_index *ix, void *stream);
 /* sticky error flag of the mailbox (a peer did not deliver within 20 s); synchronises */
 int cb_flatip_p2p_status(cb_index *ix, int *error);
 

@@ -94,6 +94,17 @@ def main():
             assert (I0.cpu().numpy() == I1).all()
             checked += 1
         if transport == "p2p":
+            # the pipelined form: 31 different queries in flight two at a time, each into its own output
+            qs = [torch.from_numpy(xq[i % 40:i % 40 + 1]).to(dev) for i in range(31)]
+            outs = [ds.submit(qq, 64) for qq in qs]
+            ds.join()
+            torch.cuda.synchronize()
+            if rank == 0:
+                for i, (D, I) in enumerate(outs):
+                    D1, I1 = whole.search(xq[i % 40:i % 40 + 1], 64)
+                    assert (I.cpu().numpy() == I1).all(), f"submit #{i}: ids differ from the unsharded index"
+                    assert (D.cpu().numpy().view(np.uint32) == D1.view(np.uint32)).all()
+                checked += 1
             assert ds.p2p_error() == 0
         dist.barrier()
     if rank == 0:

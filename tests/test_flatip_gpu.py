@@ -239,6 +239,28 @@ def test_logical_shards_equal_single_shard_bitwise(faiss, db100k, R):
     np.testing.assert_array_equal(many.reconstruct_n(19_990, 30), one.reconstruct_n(19_990, 30))
 
 
+def test_pipelined_submit_equals_blocking_search(faiss, db100k):
+    """cb_flatip_submit_search_device / cb_flatip_join (two lanes, half the SMs' residency each): a stream of
+    different queries returns exactly what the blocking search returns, for single queries (scan kernel) and
+    small batches (tensor-core path)."""
+    import torch
+    from clipb200 import sharded
+    index = faiss.IndexFlatIP(512, storage="f16", devices=[0])
+    index.add(db100k)
+    ds = sharded.DistributedFlatIP(index=index, device=torch.device("cuda", 0))
+    ds.finalize()
+    xq = synth.unit_rows(64, seed=71, clip_like=True)
+    for nq, k in ((1, 100), (1, 7), (3, 21), (32, 50)):
+        qs = [torch.from_numpy(xq[i:i + nq].copy()).cuda() for i in range(0, 64 - nq + 1, max(nq, 3))]
+        outs = [ds.submit(q, k) for q in qs]
+        ds.join()
+        torch.cuda.synchronize()
+        for q, (D, I) in zip(qs, outs):
+            D0, I0 = index.search(q.cpu().numpy(), k)
+            assert (I.cpu().numpy() == I0).all()
+            assert (D.cpu().numpy().view(np.uint32) == D0.view(np.uint32)).all()
+
+
 def test_full_size_properties():
     """BASELINE config 3 scale on one GPU (10M x 512 fp16 = 10.24 GB): size-independent
     properties -- sorted, unique ids, returned scores re-derive from the rows, and exactly
