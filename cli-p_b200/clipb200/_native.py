@@ -42,6 +42,7 @@ SIGNATURES = {
     "cb_flatip_p2p_connect": (_int, [_p, _p]),
     "cb_flatip_search_p2p_device": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p]),
     "cb_flatip_p2p_status": (_int, [_p, C.POINTER(_int)]),
+    "cb_flatip_search_p2p": (_int, [_p, _i64, _p, _i64, _p, _p, _i64]),
     "cb_flatip_submit_search_device": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p]),
     "cb_flatip_join": (_int, [_p, _p]),
     "cb_sharded_create": (_int, [_int, _int, _int, C.POINTER(_int), C.POINTER(_p)]),

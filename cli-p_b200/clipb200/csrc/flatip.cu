@@ -1357,6 +1357,36 @@ int cb_flatip_search_p2p_device(cb_index *ix, int64_t nq, const float *q_dev, in
     return CB_OK;
 }
 
+// Host-buffer form of the sharded search (the call a host program makes per query): pinned staging, H2D of
+// the query, the rank's kernel chain, and on rank 0 the merge, D2H and one synchronisation.
+int cb_flatip_search_p2p(cb_index *ix, int64_t nq, const float *q_host, int64_t k, float *D_host, int64_t *I_host,
+                         int64_t id_base) {
+    CB_REQUIRE(ix != nullptr, "cb_flatip_search_p2p: null index");
+    CB_REQUIRE(ix->p2p.attached, "cb_flatip_search_p2p: not attached (cb_flatip_p2p_init / _connect)");
+    CB_REQUIRE(nq > 0 && k > 0, "cb_flatip_search_p2p: nq and k must be > 0");
+    CB_REQUIRE(q_host != nullptr, "cb_flatip_search_p2p: null query");
+    const bool root = ix->p2p.rank == 0;
+    CB_REQUIRE(!root || (D_host && I_host), "cb_flatip_search_p2p: the root needs output buffers");
+    DeviceGuard g(ix->device);
+    int rc;
+    if ((rc = ensure_q(ix, nq))) return rc;
+    if (root && (rc = ensure_out(ix, nq * k))) return rc;
+    memcpy(ix->h_q, q_host, (size_t)nq * ix->d * 4);
+    CB_CUDA(cudaMemcpyAsync(ix->d_q, ix->h_q, (size_t)nq * ix->d * 4, cudaMemcpyHostToDevice, ix->stream));
+    rc = cb_flatip_search_p2p_device(ix, nq, ix->d_q, k, ix->d_D, ix->d_I, id_base, ix->stream);
+    if (rc) return rc;
+    if (root) {
+        CB_CUDA(cudaMemcpyAsync(ix->h_D, ix->d_D, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CB_CUDA(cudaMemcpyAsync(ix->h_I, ix->d_I, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ix->stream));
+    }
+    CB_CUDA(cudaStreamSynchronize(ix->stream));      // the staged query must not be overwritten by the next call
+    if (root) {
+        memcpy(D_host, ix->h_D, (size_t)nq * k * 4);
+        memcpy(I_host, ix->h_I, (size_t)nq * k * 8);
+    }
+    return CB_OK;
+}
+
 // Pipelined form: queue one search and return.  Searches alternate between two lanes (own stream, workspace
 // and mailbox slot); each lane's kernels take half of the SMs' residency, so the selection / exchange / merge
 // tail of one query overlaps the pass over the shard of the next.  Works with or without an attached mailbox.

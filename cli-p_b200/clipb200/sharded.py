@@ -164,6 +164,24 @@ class DistributedFlatIP:
                                                     self.id_base, C.c_void_p(stream)))
         return D, I
 
+    def search_host(self, q, k: int):
+        """numpy (nq, d) float32 in, numpy (D, I) out on rank 0 ((None, None) elsewhere): ONE C call per query
+        batch (pinned staging, H2D, kernel chain, peer delivery, merge, D2H, one synchronisation)."""
+        import numpy as np
+        from . import _native as N
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        nq = q.shape[0]
+        if self.world == 1 or self.transport != "p2p":
+            Dt, It = self.search(torch.from_numpy(q).to(self.device), k)
+            return (Dt.cpu().numpy(), It.cpu().numpy()) if Dt is not None else (None, None)
+        D = I = None
+        dp = ip = None
+        if self.rank == 0:
+            D, I = np.empty((nq, k), np.float32), np.empty((nq, k), np.int64)
+            dp, ip = C.c_void_p(D.ctypes.data), C.c_void_p(I.ctypes.data)
+        N.check(N.lib().cb_flatip_search_p2p(self._handle(), nq, C.c_void_p(q.ctypes.data), k, dp, ip, self.id_base))
+        return D, I
+
     # ---- pipelined query stream ---------------------------------------------------------------------
     def submit(self, q: torch.Tensor, k: int, out=None):
         """Queue one search and return at once (cb_flatip_submit_search_device): consecutive submissions

@@ -130,6 +130,9 @@ int cb_flatip_p2p_connect(cb_index *ix, const void *root_ipc_handle64);
  * max_elems per mailbox slot; k <= max_elems. */
 int cb_flatip_search_p2p_device(cb_index *ix, int64_t nq, const float *q_dev, int64_t k, float *D_dev,
                                 int64_t *I_dev, int64_t id_base, void *stream);
+/* host-buffer form: q_host in, (D_host, I_host) out on rank 0 (may be NULL elsewhere); returns when done */
+int cb_flatip_search_p2p(cb_index *ix, int64_t nq, const float *q_host, int64_t k, float *D_host,
+                         int64_t *I_host, int64_t id_base);
 /* Pipelined form for query streams: queue one search and return; results are ordered on a stream by
  * cb_flatip_join.  Searches alternate between two lanes (own stream, workspace and mailbox slot) and each
  * lane's kernels take half of the SMs' residency, so the selection / exchange / merge tail of one query

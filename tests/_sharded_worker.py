@@ -94,6 +94,12 @@ def main():
             assert (I0.cpu().numpy() == I1).all()
             checked += 1
         if transport == "p2p":
+            Dh, Ih = ds.search_host(xq[:3], 21)               # host-buffer entry point
+            if rank == 0:
+                D1, I1 = whole.search(xq[:3], 21)
+                assert (Ih == I1).all() and (Dh.view(np.uint32) == D1.view(np.uint32)).all()
+            else:
+                assert Dh is None and Ih is None
             # the pipelined form: 31 different queries in flight two at a time, each into its own output
             qs = [torch.from_numpy(xq[i % 40:i % 40 + 1]).to(dev) for i in range(31)]
             outs = [ds.submit(qq, 64) for qq in qs]
