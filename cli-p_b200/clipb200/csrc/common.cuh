@@ -31,6 +31,7 @@ enum Tune : int {
     T_SKIP,               // CLIPB200_SKIP               (only in -DCLIPB200_EXPERIMENTS builds)
     T_PDL,                // CLIPB200_PDL                0: no programmatic dependent launch between the towers' kernels
     T_GEMM_SKINNY,        // CLIPB200_GEMM_SKINNY        0: single-row-block GEMMs (M <= 128) use the general kernel; n > 0: force split n
+    T_GEMM_RESID_STAGES,  // CLIPB200_GEMM_RESID_STAGES  ring depth of the residual-epilogue GEMMs (their staging boxes leave less room)
     T_COUNT
 };
 int64_t tune(Tune t);
@@ -91,8 +92,7 @@ struct DeviceGuard {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// launch with optional cluster dimension and (unless the pdl knob is 0 or the stream is being captured
-// into a CUDA graph) the programmatic-serialization attribute
+// launch with optional cluster dimension and (unless the pdl knob is 0) the programmatic-serialization attribute
 template <typename... KArgs, typename... Args>
 cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
                       bool pdl, Args &&...args) {
@@ -111,8 +111,11 @@ cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
         na++;
     }
     if (pdl && tune(T_PDL) != 0) {
+        // the attribute is kept inside CUDA-graph captures too (programmatic edges: single-query encode_image
+        // 0.486 -> 0.432 ms, encode_text 0.406 -> 0.334 ms, profiles/r02_latency_pdl_in_graph.txt); pdl = 2 drops
+        // it there
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        if (tune(T_PDL) != 2 &&          // pdl = 2: keep the attribute inside CUDA-graph captures as well
+        if (tune(T_PDL) == 2 &&
             cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
         if (cs == cudaStreamCaptureStatusNone) {
             attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;

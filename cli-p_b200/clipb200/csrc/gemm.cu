@@ -781,6 +781,7 @@ int launch(const GemmArgs &g, cudaStream_t s) {
     const int clusters = std::min(m_tiles * n_tiles, sms / NCTA);
     int stages = C::STAGES;
     if (tune(T_GEMM_STAGES) > 0) stages = std::max(2, std::min(C::STAGES, (int)tune(T_GEMM_STAGES)));
+    if (EPI == EPI_BIAS_RESID && tune(T_GEMM_RESID_STAGES) > 0) stages = std::max(2, std::min(stages, (int)tune(T_GEMM_RESID_STAGES)));
 #ifdef CLIPB200_EXPERIMENTS
     if (tune(T_GEMM_DEBUG) > 0) stages |= (int)tune(T_GEMM_DEBUG) << 8;
 #endif

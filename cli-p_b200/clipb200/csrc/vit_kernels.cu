@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t *__res
 // one thread = 4 pixels x 3 channels of an NCHW fp32 image
 __global__ void __launch_bounds__(256) preprocess_f32_kernel(const float *__restrict__ img,
                                                             __half *__restrict__ patches, int B) {
+    pdl_wait();
     const int64_t total = (int64_t)B * 224 * 56;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -93,6 +94,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half *__restrict
     const int lane = threadIdx.x & 31;
     const int stride = gridDim.x * (blockDim.x >> 5);
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();                     // programmatic dependent launch (common.cuh): inputs come from the previous kernel
+    pdl_launch_dependents();
     if (row >= rows) return;
 
     auto src_row = [&](int r) -> int64_t { return gather ? (int64_t)gather[r] : (int64_t)r * in_row_stride; };
@@ -174,6 +177,8 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float *__restrict__ i
                                                     int width) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_launch_dependents();
     if (row >= rows) return;
     const float4 *p = reinterpret_cast<const float4 *>(in + (size_t)row * width);
     float4 *o = reinterpret_cast<float4 *>(out + (size_t)row * width);
@@ -197,6 +202,8 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const int32_t *__restri
                                                         float *__restrict__ stats_out) {
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    pdl_wait();
+    pdl_launch_dependents();
     const int32_t *row = ids + (size_t)b * ctx;
     if (warp == 0) {
         int best = INT_MIN, best_t = 0;
@@ -252,7 +259,7 @@ int preprocess_u8(const uint8_t *img, __half *patches, int B, cudaStream_t s) {
     return CB_OK;
 }
 int preprocess_f32(const float *img, __half *patches, int B, cudaStream_t s) {
-    preprocess_f32_kernel<<<grid_for((int64_t)B * 224 * 56, 256), 256, 0, s>>>(img, patches, B);
+    CB_CUDA(launch_ex(preprocess_f32_kernel, dim3(grid_for((int64_t)B * 224 * 56, 256)), dim3(256), 0, s, 1, true, img, patches, B));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -266,23 +273,26 @@ int layernorm_f16(const __half *in, __half *out, const float *gamma, const float
     const int grid = std::min((rows + 7) / 8, kNumSMs * per_sm);
     if (cls_period <= 0) cls_period = 1;
     if (width == 768)
-        layernorm_kernel<768><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period, stats_out);
+        CB_CUDA(launch_ex(layernorm_kernel<768>, dim3(grid), dim3(256), 0, s, 1, true, in, out, gamma, beta, rows, in_row_stride,
+                          gather, cls_fill, cls_period, stats_out));
     else
-        layernorm_kernel<512><<<grid, 256, 0, s>>>(in, out, gamma, beta, rows, in_row_stride, gather, cls_fill, cls_period, stats_out);
+        CB_CUDA(launch_ex(layernorm_kernel<512>, dim3(grid), dim3(256), 0, s, 1, true, in, out, gamma, beta, rows, in_row_stride,
+                          gather, cls_fill, cls_period, stats_out));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
 int l2norm_rows_f32(const float *in, float *out, int rows, int width, cudaStream_t s) {
     CB_REQUIRE(width % 4 == 0, "l2norm_rows_f32: width must be a multiple of 4");
     if (rows == 0) return CB_OK;
-    l2norm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, out, rows, width);
+    CB_CUDA(launch_ex(l2norm_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, 1, true, in, out, rows, width));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
 int text_embed(const int32_t *ids, const float *tok_emb, const float *pos_emb, __half *x, int *eot_row, int B,
                int ctx, int width, int vocab, cudaStream_t s, float *stats_out) {
     if (B == 0) return CB_OK;
-    text_embed_kernel<<<B, 256, 0, s>>>(ids, tok_emb, pos_emb, x, eot_row, ctx, width, vocab, stats_out);
+    CB_CUDA(launch_ex(text_embed_kernel, dim3(B), dim3(256), 0, s, 1, true, ids, tok_emb, pos_emb, x, eot_row, ctx, width, vocab,
+                      stats_out));
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
