@@ -834,7 +834,8 @@ int launch_skinny(const GemmArgs &g, int split, cudaStream_t s) {
 // single-query encode_image takes 0.476 ms with split 1, 0.529 / 0.585 / 0.601 ms with split 2 / 4 / 8 (general
 // kernel: 0.487 ms).  The ~7 us per launch of a single-query forward pass is launch + prologue + one HBM round
 // trip + epilogue, not the serial walk over K: the cluster barrier and the scratch round trip cost more than the
-// shorter k-loop saves.  The default is therefore NO split; the knob gemm_skinny = 2 / 4 / 8 forces one (tests).
+// shorter k-loop saves -- also when only the long-K shapes (c_proj, patch embed) are split: image unchanged,
+// text 0.333 -> 0.373 ms.  The default is therefore NO split; the knob gemm_skinny = 2 / 4 / 8 forces one (tests).
 int skinny_split(const GemmArgs &g, int sms) {
     (void)sms;
     if (g.skinny_scratch == nullptr) return 1;
