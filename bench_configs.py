@@ -111,7 +111,7 @@ def run_config0(emit, n_images=1000):
         sd = weights.synthetic_state_dict(0)
         model = clip.CLIPB200(sd, device=torch.cuda.current_device(), max_image_batch=256, max_text_batch=1)
         tokens = clip_ref.synthetic_tokens(1, seed=4)
-        res = {}
+        res, ranked = {}, {}
         for mode, kw in (("pillow", {}), ("nvjpeg", {"decode": "nvjpeg"})):
             work = os.path.join(tmp, mode)
             os.makedirs(work)
@@ -141,9 +141,26 @@ def run_config0(emit, n_images=1000):
             rows = searcher.results(searcher.features_for_tokens(tokens), k=20, offset=0)
             t_query = time.perf_counter() - tq
             res[mode] = {"embedded": ok, "failed": bad, "embed_s": t_embed, "images_per_s": ok / t_embed,
-                         "build_index_s": t_index, "text_query_top20_ms": t_query * 1e3, "top1_id": rows[0][1]}
+                         "build_index_s": t_index, "text_query_top20_ms": t_query * 1e3, "top1_id": rows[0][1],
+                         # the ranking the user sees: (score, id) of the first five rows, and the gap between them
+                         "top5": [(round(r[0], 6), r[1]) for r in rows[:5]],
+                         "top1_minus_top2": rows[0][0] - rows[1][0]}
+            ranked[mode] = {r[1]: (j, r[0]) for j, r in enumerate(rows)}
             env.close()
         os.chdir(cwd)
+        if "pillow" in ranked and "nvjpeg" in ranked:
+            # nvjpeg and libjpeg-turbo are different decoders (pixels differ by a level or two), so the stored
+            # vectors differ at cosine ~0.9999 and near-tied neighbours can swap.  Say how near: where does the
+            # Pillow path's top-1 land in the nvjpeg ranking, and how far apart are the scores involved?
+            p1 = res["pillow"]["top1_id"]
+            n1 = res["nvjpeg"]["top1_id"]
+            res["top1_agreement"] = {
+                "same_top1": p1 == n1,
+                "pillow_top1_in_nvjpeg_ranking": ranked["nvjpeg"].get(p1, (None, None)),
+                "nvjpeg_top1_in_pillow_ranking": ranked["pillow"].get(n1, (None, None)),
+                "pillow_top1_minus_top2": res["pillow"]["top1_minus_top2"],
+                "note": "a swap is a near-tie (score gap below the ~1e-3 the decoders' pixel differences move a "
+                        "score), not a retrieval error; the default decode path is Pillow, the reference's pixels"}
         # the reference's loop on the host cores: transform + encode_image one image at a time
         torch.set_num_threads(os.cpu_count() or 1)
         transform = clip._transform(224)
