@@ -21,7 +21,8 @@ void set_error(const char *fmt, ...) {
 // ---- tuning knobs ---------------------------------------------------------------------
 static const char *const kTuneNames[T_COUNT] = {
     "gemm_bn", "gemm_ncta", "gemm_stages", "gemm_raster", "batch_min_nq", "no_graph",
-    "ln_blocks_per_sm", "ln_fold", "gemm_debug", "skip", "pdl", "gemm_skinny", "gemm_resid_stages"};
+    "ln_blocks_per_sm", "ln_fold", "gemm_debug", "skip", "pdl", "gemm_skinny", "gemm_resid_stages",
+    "attn_tc"};
 static std::atomic<int64_t> g_tune[T_COUNT];
 
 // environment -> table, once, at load time (CLIPB200_<NAME IN CAPITALS>)

@@ -32,6 +32,7 @@ enum Tune : int {
     T_PDL,                // CLIPB200_PDL                0: no programmatic dependent launch between the towers' kernels
     T_GEMM_SKINNY,        // CLIPB200_GEMM_SKINNY        0: single-row-block GEMMs (M <= 128) use the general kernel; n > 0: force split n
     T_GEMM_RESID_STAGES,  // CLIPB200_GEMM_RESID_STAGES  ring depth of the residual-epilogue GEMMs (their staging boxes leave less room)
+    T_ATTN_TC,            // CLIPB200_ATTN_TC            0: vision-tower attention on the mma.sync kernel instead of the tcgen05 pair kernel
     T_COUNT
 };
 int64_t tune(Tune t);

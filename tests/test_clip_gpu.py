@@ -98,6 +98,30 @@ def test_attention_kernel(L, heads, causal):
     assert (out.float() - ref).abs().max().item() <= 4e-3
 
 
+@pytest.mark.parametrize("B", [2, 3, 8, 61, 256])
+def test_vision_attention_pair_kernel(B):
+    """The tcgen05 kernel that puts two images of a head on one 128-row tile (odd batches: a lone last
+    image) against fp32 torch, and against the mma.sync kernel it replaces (knob attn_tc = 0).  Inputs
+    carry a few large scores so that the softmax is peaked for some rows and flat for others."""
+    import torch
+    from clipb200 import _native as N
+    L, heads, W = 50, 12, 768
+    g = torch.Generator(device="cuda").manual_seed(B)
+    qkv = (torch.randn((B * L, 3 * W), generator=g, device="cuda") * 1.5)
+    qkv[::7, :W] *= 4.0                                                  # peaked rows
+    qkv = qkv.half()
+    out = torch.full((B * L, W), float("nan"), dtype=torch.float16, device="cuda")
+    N.check(N.lib().cb_attention_f16_device(_p(qkv), _p(out), B, L, heads, 0, _stream(torch)))
+    old = torch.empty_like(out)
+    with N.tuning(attn_tc=0):
+        N.check(N.lib().cb_attention_f16_device(_p(qkv), _p(old), B, L, heads, 0, _stream(torch)))
+    q, k, v = qkv.float().view(B, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, W)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= 4e-3
+    assert (out.float() - old.float()).abs().max().item() <= 4e-3
+
+
 def test_preprocess_kernels():
     import torch
     from clipb200 import _native as N
