@@ -182,19 +182,20 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
 // kernel is bound by the 128 B/clk shared-memory port, and P through shared memory was a quarter of its
 // traffic).  O[128 x 64] = P x [V_A ; V_B], V an MN-major operand straight from the row-major TMA image.  The
 // cross terms of S and the zero blocks of P are wasted tensor work (the pipe is idle anyway).  O overwrites
-// S in tensor memory; the fp16 output tile leaves by TMA store.  CTAs are persistent (three per SM); a fifth
-// warp's elected thread issues every TMA and MMA and fetches the next unit's Q, K as soon as S exists and
+// S in tensor memory; the fp16 output tile leaves by TMA store.  CTAs are persistent, one per SM, with four
+// independent groups (all 512 tensor-memory columns); per group a fifth warp's elected thread issues every TMA and MMA and fetches the next unit's Q, K as soon as S exists and
 // its V as soon as O does; the row threads and that thread hand over through mbarriers only.
 namespace pair {
 using namespace tc;
 constexpr int L = 50;
-constexpr int kRowWarps = 4;              // one tile row per thread
-constexpr int kThreads = (kRowWarps + 1) * 32;   // + the warp whose elected thread issues TMA and MMA
+constexpr int kGroups = 4;                // independent pipelines per CTA: each owns 128 tensor-memory columns and a Q/K/V stage
+constexpr int kRowWarps = 4;              // per group: one tile row per thread
+constexpr int kThreads = kGroups * (kRowWarps + 1) * 32;   // + per group the warp whose elected thread issues TMA and MMA
 constexpr int kTile = 128 * 128;             // bytes of a 128-row x 64-half tile (also two 64-row tiles)
 constexpr int kHalf = kTile / 2;             // image B's rows start here
 constexpr int kImgBytes = L * HD * 2;        // one TMA box: 50 rows x 128 B
-constexpr int kCtasPerSM = 3;
-constexpr int kSmem = 4 * kTile + 1024 /*alignment*/ + 128 /*barriers + tmem slot*/;   // Q, K, V, P/output: 65.7 KB
+constexpr int kStage = 3 * kTile;         // Q, K, V of one group (the output tile reuses V): 48 KB
+constexpr int kSmem = kGroups * kStage + 1024 /*alignment*/ + kGroups * 64 + 64 /*barriers + tmem slot*/;
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t *v) {
     asm volatile(
@@ -218,6 +219,25 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t *v) {
           "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
+}
+// tight poll (mbarrier.test_wait): the hand-overs of this kernel are a few hundred clocks apart, so the
+// suspend time of try_wait would be a visible part of every round trip
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > kSpinLimit) __trap();
+    }
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]: A is fp16, two K elements per 32-bit column, one row per lane
@@ -246,53 +266,61 @@ constexpr uint32_t kIdescS = make_idesc(128, 128);                 // Q, K both 
 constexpr uint32_t kIdescO = make_idesc(128, 64) | (1u << 16);     // P K-major (tensor memory), V MN-major
 constexpr uint32_t kPCol = 64;                                     // P: tensor-memory columns 64..127 (fp16 pairs of 128 keys)
 
-__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+__global__ void __launch_bounds__(kThreads, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, int B,
                       int heads, int units) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sQ = smem, *sK = smem + kTile, *sV = smem + 2 * kTile, *sPO = smem + 3 * kTile;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 4 * kTile);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int W = heads * HD;
+    // warps 0 .. 4 kGroups - 1: row warps, four per group (warp % 4 = the TMEM lane quadrant a warp may touch);
+    // warps 4 kGroups ..: one issuing warp per group
+    const bool is_row = warp < kGroups * kRowWarps;
+    const int grp = is_row ? warp / kRowWarps : warp - kGroups * kRowWarps;
+    uint8_t *sQ = smem + grp * kStage, *sK = sQ + kTile, *sV = sQ + 2 * kTile;
+    uint8_t *sPO = sV;                // the fp16 output tile is written over V once O exists
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kGroups * kStage) + grp * 8;
     uint64_t *full_qk = bars + 0;     // Q, K landed (TMA bytes)
     uint64_t *full_v = bars + 1;      // V landed
     uint64_t *s_done = bars + 2;      // S in tensor memory (MMA commit)
     uint64_t *o_done = bars + 3;      // O in tensor memory (MMA commit): P and V are consumed
-    uint64_t *po_free = bars + 4;     // the previous unit's store has read the output tile
-    uint64_t *p_ready = bars + 5;     // 128 arrivals: P in tensor memory, S read
-    uint64_t *o_ready = bars + 6;     // 128 arrivals: output tile written, O read
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+    uint64_t *p_ready = bars + 4;     // 128 arrivals: P in tensor memory, S read
+    uint64_t *o_ready = bars + 5;     // 128 arrivals: output tile written, O read
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kGroups * kStage + kGroups * 64);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int W = heads * HD;
-
-    if (warp == kRowWarps) {
+    if (!is_row) {
         if (elect_one()) {
-            for (int i = 0; i < 5; i++) mbar_init(bars + i, 1);
+            for (int i = 0; i < 4; i++) mbar_init(bars + i, 1);
             mbar_init(p_ready, kRowWarps * 32);
             mbar_init(o_ready, kRowWarps * 32);
             fence_barrier_init();
-            tma_prefetch_desc(&tm_qkv);
-            tma_prefetch_desc(&tm_out);
+            if (grp == 0) {
+                tma_prefetch_desc(&tm_qkv);
+                tma_prefetch_desc(&tm_out);
+            }
         }
-    } else if (warp == 1) {
-        tmem_alloc<1>(tmem_slot, 128);
+    } else if (warp == 0) {
+        tmem_alloc<1>(tmem_slot, 512);
     }
     // Rows of V the loads never write (tokens 50..63 of either image; the whole second tile when the batch is
     // odd) must be finite: P is exactly 0 there, and 0 x NaN is not.  Zeroed once; the loads come after the barrier.
-    for (int i = tid; i < kTile / 16; i += kThreads) reinterpret_cast<uint4 *>(sV)[i] = make_uint4(0, 0, 0, 0);
+    for (int g = 0; g < kGroups; g++)
+        for (int i = tid; i < kTile / 16; i += kThreads) reinterpret_cast<uint4 *>(smem + g * kStage + 2 * kTile)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = *tmem_slot + (uint32_t)(grp * 128);        // this group's 128 columns
     // Dependents are released as soon as every CTA of this grid is resident (none is left to schedule, so a
     // dependent that parks on an SM with its shared and tensor memory cannot starve this grid); they wait for
     // this grid's completion in their own griddepcontrol.wait before touching global memory.
     pdl_launch_dependents();
     pdl_wait();                     // qkv comes from the previous kernel of the stream
 
-    // unit u = (pair of images, head); this CTA takes u = blockIdx.x, + gridDim.x, ...
-    if (warp == kRowWarps) {
+    // unit u = (pair of images, head); group g of CTA c takes u = g gridDim.x + c, + kGroups gridDim.x, ... (the
+    // left-over units of the last round spread over CTAs, not over the groups of a few)
+    const int u0 = grp * gridDim.x + blockIdx.x, ustride = gridDim.x * kGroups;
+    if (!is_row) {
         // ---- one thread: TMA loads, both MMAs, the output store -------------------------------------
         if (elect_one()) {
             auto load_qk = [&](int u) {
@@ -314,32 +342,32 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 if (hasB) tma_load_2d(sV + kHalf, &tm_qkv, 2 * W + h * HD, (imgA + 1) * L, full_v);
             };
             auto issue_s = [&](uint32_t ph) {                         // S = Q K^T once Q, K have landed
-                mbar_wait(full_qk, ph);
+                mbar_spin(full_qk, ph);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < HD / 16; k++)
                     umma_f16<1>(tmem, make_smem_desc(smem_u32(sQ) + k * 32), make_smem_desc(smem_u32(sK) + k * 32), kIdescS, k > 0);
                 umma_commit<1>(s_done);
             };
-            load_qk(blockIdx.x);
-            load_v(blockIdx.x);
-            issue_s(0);
+            if (u0 < units) {
+                load_qk(u0);
+                load_v(u0);
+                issue_s(0);
+            }
             uint32_t ph = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x, ph ^= 1) {
-                const int un = u + gridDim.x;                         // this CTA's next unit
+            for (int u = u0; u < units; u += ustride, ph ^= 1) {
+                const int un = u + ustride;                           // this group's next unit
                 const int pr = u / heads, h = u % heads, imgA = 2 * pr;
-                mbar_wait(s_done, ph);                                // Q, K consumed: fetch the next unit's
+                mbar_spin(s_done, ph);                                // Q, K consumed: fetch the next unit's
                 if (un < units) load_qk(un);
-                mbar_wait(p_ready, ph);                               // P in shared memory, S read by every row
-                mbar_wait(full_v, ph);
+                mbar_spin(p_ready, ph);                               // P in shared memory, S read by every row
+                mbar_spin(full_v, ph);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 128 / 16; k++)
                     umma_f16_ts(tmem, tmem + kPCol + k * 8, make_smem_desc_mn(smem_u32(sV) + k * 2048), kIdescO, k > 0);
                 umma_commit<1>(o_done);
-                mbar_wait(o_done, ph);                                // V consumed
-                if (un < units) load_v(un);
-                mbar_wait(o_ready, ph);                               // output tile complete, O read by every row
+                mbar_spin(o_ready, ph);                               // output tile (over V) complete, O read by every row
                 if (un < units) issue_s(ph ^ 1);                      // the next S overwrites O
                 else tc_fence_after();
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -349,23 +377,24 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                                  ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(smem_u32(sPO) + kHalf), "r"(h * HD), "r"((imgA + 1) * L) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                mbar_arrive(po_free);
+                if (un < units) load_v(un);                           // the tile is read: V's buffer is free
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
         __syncwarp();
     } else {
         // ---- 128 threads: one row of the tile each ---------------------------------------------------
-        const int img = tid >> 6, tok = tid & 63;
-        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+        const int row = tid & 127;                                    // row of the group's tile
+        const int img = row >> 6, tok = row & 63;
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t trow = tlane + (uint32_t)(img * 64);          // S: the own image's keys
-        const uint32_t prow = smem_u32(sPO) + tid * 128;              // this thread's row of the output tile
+        const uint32_t prow = smem_u32(sPO) + row * 128;              // this thread's row of the output tile
         const float sl2 = 0.125f * 1.4426950408889634f;              // 1/sqrt(64) folded into the exp2 argument
         uint32_t ph = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ph ^= 1) {
+        for (int u = u0; u < units; u += ustride, ph ^= 1) {
             const bool hasB = 2 * (u / heads) + 1 < B;
             const bool valid = tok < L && (img == 0 || hasB);
-            mbar_wait(s_done, ph);
+            mbar_spin(s_done, ph);
             tc_fence_after();
             uint32_t sr[52];
             {
@@ -375,11 +404,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 tmem_ld_x2(trow + 48, &sr[48]);
                 tmem_ld_wait();
             }
-            float m = __uint_as_float(sr[0]);
+            float m4[4] = {__uint_as_float(sr[0]), __uint_as_float(sr[1]), __uint_as_float(sr[2]), __uint_as_float(sr[3])};
 #pragma unroll
-            for (int j = 1; j < L; j++) m = fmaxf(m, __uint_as_float(sr[j]));
+            for (int j = 4; j < L; j++) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(sr[j]));   // four chains, not one of 49
+            const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             const float c = -m * sl2;
-            float sum = 0.f;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t pk[32];                                          // 64 keys as fp16 pairs; keys 50..63 are 0
 #pragma unroll
             for (int j = 0; j < L; j += 2) {
@@ -387,9 +417,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(sr[j]), sl2, c)));
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(sr[j + 1]), sl2, c)));
                 if (!valid) p0 = p1 = 0.f;                            // padding rows: S is garbage there
-                sum += p0 + p1;
+                s4[(j >> 1) & 3] += p0 + p1;
                 pk[j >> 1] = pack_h2(p0, p1);
             }
+            const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             // P of this row, block-diagonal over the 128 keys of both images: the own image's 32 pairs (keys
             // 50..63 zero), zeros for the other image's keys.  It overwrites columns of S only this thread
             // reads (its own lane), and lies outside the 64 columns O is written to.
@@ -404,10 +435,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             tc_fence_before();
             mbar_arrive(p_ready);
 
-            mbar_wait(o_done, ph);
+            mbar_spin(o_done, ph);
             tc_fence_after();
-            const float inv = 1.0f / sum;
-            if (u != (int)blockIdx.x) mbar_wait(po_free, ph ^ 1);     // the previous unit's store has read the tile
+            const float inv = valid ? 1.0f / sum : 0.f;               // padding rows stay zero: the tile lies over V, whose
+                                                                      // padding rows must stay finite for the next unit
 #pragma unroll
             for (int half = 0; half < 2; half++) {                    // this row of O, normalised, fp16
                 uint32_t o[32];
@@ -420,7 +451,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                     v.y = pack_h2(__uint_as_float(o[8 * ch + 2]) * inv, __uint_as_float(o[8 * ch + 3]) * inv);
                     v.z = pack_h2(__uint_as_float(o[8 * ch + 4]) * inv, __uint_as_float(o[8 * ch + 5]) * inv);
                     v.w = pack_h2(__uint_as_float(o[8 * ch + 6]) * inv, __uint_as_float(o[8 * ch + 7]) * inv);
-                    sts128(prow + (((half * 4 + ch) ^ (tid & 7)) << 4), v);
+                    sts128(prow + (((half * 4 + ch) ^ (row & 7)) << 4), v);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -430,9 +461,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc<1>(tmem, 128);
+        tmem_dealloc<1>(*tmem_slot, 512);
     }
 }
 
@@ -474,15 +505,15 @@ int launch(const __half *qkv, __half *out, int B, int heads, cudaStream_t s) {
     cudaError_t err = cudaSuccess;
     std::call_once(once[dev & 63], [&] {
         err = cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        // three CTAs per SM need 200 KB of the 228: ask for the largest shared-memory carve-out
+        // 193 KB of the 228: ask for the largest shared-memory carve-out
         if (err == cudaSuccess)
             err = cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     });
     CB_CUDA(err);
-    // persistent: the grid scheduler starts ~1 CTA per 8 clocks GPU-wide, so one CTA per (pair, head) would spend
-    // longer being launched (1536 CTAs: 6.4 us) than computing
+    // persistent, one CTA per SM: the grid scheduler starts ~1 CTA per 8 clocks GPU-wide, so one CTA per (pair, head)
+    // would spend longer being launched (1536 CTAs: 6.4 us) than computing, and even four thin CTAs per SM ramp for 2.7 us
     const int units = ((B + 1) / 2) * heads;
-    const int grid = std::min(units, kCtasPerSM * kNumSMs);
+    const int grid = std::min((units + kGroups - 1) / kGroups, kNumSMs);
     CB_CUDA(launch_ex(attention_pair_kernel, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmem, s, 1, true, tq, to, B, heads, units));
     return CB_OK;
 }
