@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 template <int L, bool CAUSAL>
 __global__ void __launch_bounds__(((L + 15) / 16) * 32, L <= 64 ? 8 : 6)
-attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int heads) {
+attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int heads, int pairs) {
     constexpr int KT = (L + 15) / 16;   // 16-key steps (= 16-row query tiles = warps)
     constexpr int LP = KT * 16;         // padded sequence
     constexpr int NT = 2 * KT;          // 8-key score tiles
@@ -63,10 +63,13 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
     __shared__ __align__(16) __half sbuf[(2 * L + LP) * LDS];
     __half *sQ = sbuf, *sK = sbuf + L * LDS, *sV = sbuf + 2 * L * LDS;
 
-    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int W = heads * HD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_wait();                     // qkv comes from the previous kernel of the stream (common.cuh)
+    // the grid is capped at what is resident at once; a CTA walks over (sequence, head) pairs
+    for (int pairi = blockIdx.x; pairi < pairs; pairi += gridDim.x) {
+    const int b = pairi / heads, h = pairi % heads;
+    if (pairi != (int)blockIdx.x) __syncthreads();                    // the previous pair's tiles are consumed
 
     // stage q|k|v of this head: 3 x LP rows x 8 chunks of 16 B, global -> shared with cp.async (no register
     // round trip); rows >= L of V are zero.  blockDim = 8 chunks x (4 KT) rows, so iteration `it` of the
@@ -170,6 +173,7 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
         const int col = h * HD + dt * 8 + (lane & 3) * 2;
         if (r0 < L) *reinterpret_cast<uint32_t *>(out + (size_t)(b * L + r0) * W + col) = pack2(o[dt][0] * i0, o[dt][1] * i0);
         if (r1 < L) *reinterpret_cast<uint32_t *>(out + (size_t)(b * L + r1) * W + col) = pack2(o[dt][2] * i1, o[dt][3] * i1);
+    }
     }
     pdl_launch_dependents();
 }
@@ -510,8 +514,8 @@ int launch(const __half *qkv, __half *out, int B, int heads, cudaStream_t s) {
             err = cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     });
     CB_CUDA(err);
-    // persistent, one CTA per SM: the grid scheduler starts ~1 CTA per 8 clocks GPU-wide, so one CTA per (pair, head)
-    // would spend longer being launched (1536 CTAs: 6.4 us) than computing, and even four thin CTAs per SM ramp for 2.7 us
+    // persistent, one CTA per SM (measured: with one CTA per unit, the CTAs of an SM started ~1200 clocks apart, and
+    // each paid barrier set-up and a tensor-memory allocation)
     const int units = ((B + 1) / 2) * heads;
     const int grid = std::min((units + kGroups - 1) / kGroups, kNumSMs);
     CB_CUDA(launch_ex(attention_pair_kernel, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmem, s, 1, true, tq, to, B, heads, units));
@@ -527,13 +531,13 @@ int attention_f16(const __half *qkv, __half *out, int B, int L, int heads, bool 
         int rc = pair::launch(qkv, out, B, heads, s);
         if (rc) return rc;
     } else if (L == 50 && !causal) {
-        CB_CUDA(launch_ex(attention_kernel<50, false>, dim3(B * heads), dim3(4 * 32), 0, s, 1, true, qkv, out, heads));
+        CB_CUDA(launch_ex(attention_kernel<50, false>, dim3(std::min(B * heads, 8 * kNumSMs)), dim3(4 * 32), 0, s, 1, true, qkv, out, heads, B * heads));
     } else if (L == 77 && causal) {
-        CB_CUDA(launch_ex(attention_kernel<77, true>, dim3(B * heads), dim3(5 * 32), 0, s, 1, true, qkv, out, heads));
+        CB_CUDA(launch_ex(attention_kernel<77, true>, dim3(std::min(B * heads, 6 * kNumSMs)), dim3(5 * 32), 0, s, 1, true, qkv, out, heads, B * heads));
     } else if (L == 77 && !causal) {
-        CB_CUDA(launch_ex(attention_kernel<77, false>, dim3(B * heads), dim3(5 * 32), 0, s, 1, true, qkv, out, heads));
+        CB_CUDA(launch_ex(attention_kernel<77, false>, dim3(std::min(B * heads, 6 * kNumSMs)), dim3(5 * 32), 0, s, 1, true, qkv, out, heads, B * heads));
     } else if (L == 50 && causal) {
-        CB_CUDA(launch_ex(attention_kernel<50, true>, dim3(B * heads), dim3(4 * 32), 0, s, 1, true, qkv, out, heads));
+        CB_CUDA(launch_ex(attention_kernel<50, true>, dim3(std::min(B * heads, 8 * kNumSMs)), dim3(4 * 32), 0, s, 1, true, qkv, out, heads, B * heads));
     } else {
         set_error("attention_f16: sequence length %d not supported (50 or 77)", L);
         return CB_ERR_INVALID;
