@@ -23,8 +23,9 @@ cap r02_gemm_cfc "gemm_tcgen05_kernel<\\(int\\)256, \\(int\\)1, \\(int\\)2>" 14 
 #    rest; two warm-up searches + one timed = 18 launches, the 16th is a 4M range)
 python profiles/search_probe.py 10000000 1024 batch 1 > /dev/null 2>&1
 cap r02_batch_kernel "flatip_batch_kernel<\\(int\\)2>" 15 python profiles/search_probe.py 10000000 1024 batch 1
-# 3b. attention of the batch-256 vision tower (12 heads x 256 images, L = 50)
-cap r02_attention "attention_kernel<\\(int\\)50, \\(bool\\)0>" 14 python profiles/embed_launch_times.py 3
+# 3b. attention of the batch-256 vision tower (12 heads x 256 images, L = 50): the tcgen05 pair kernel, a launch
+#     of a timed step (the first dozens belong to the calibration pass and the warm-up)
+cap r02_attention_pair "attention_pair_kernel" 50 python profiles/embed_launch_times.py 3
 # 4. launch lists (durations only)
 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file gpurun_out/r02_embed_launches.csv python profiles/embed_launch_times.py 3 > /dev/null 2>&1
 $NCU --metrics gpu__time_duration.sum -c 200 --csv --log-file gpurun_out/r02_search_launches.csv python profiles/search_probe.py 10000000 1,1024 auto 2 > /dev/null 2>&1

@@ -86,9 +86,11 @@ def test_tensor_core_kernels_are_tcgen05_tma_tmem(lib):
     d = sd.digest()
     names = sd.demangle(list(d))
     tc = {sd.shorten(names[k]): c for k, c in d.items()
-          if "gemm_tcgen05_kernel" in names[k] or "flatip_batch_kernel" in names[k]}
+          if "gemm_tcgen05_kernel" in names[k] or "flatip_batch_kernel" in names[k] or "attention_pair_kernel" in names[k]}
     assert len([k for k in tc if k.startswith("gemm_tcgen05_kernel")]) >= 20      # BN x epilogue x NCTA
     assert {"flatip_batch_kernel<1>", "flatip_batch_kernel<2>"} <= set(tc)
+    pair = [c for k, c in tc.items() if "attention_pair_kernel" in k]
+    assert len(pair) == 1 and pair[0]["UTCHMMA"] >= 12 and pair[0]["UTMASTG"] >= 2   # S (4) + P.V from TMEM (8), TMA stores
     for k, c in tc.items():
         assert c["UTCHMMA"] >= 4 and c["UTMALDG"] >= 2 and c["LDTM"] >= 1 and c["UTCBAR"] >= 2, (k, dict(c))
         assert c["HMMA"] == 0, f"{k} fell back to legacy mma.sync"
