@@ -527,7 +527,8 @@ int launch(const __half *qkv, __half *out, int B, int heads, cudaStream_t s) {
 
 int attention_f16(const __half *qkv, __half *out, int B, int L, int heads, bool causal, cudaStream_t s) {
     if (B == 0) return CB_OK;
-    if (L == 50 && !causal && B >= 2 && tune(T_ATTN_TC) != 0) {
+    // TMA needs 16-byte aligned tensors; a lone image would leave half of every tile empty
+    if (L == 50 && !causal && B >= 2 && tune(T_ATTN_TC) != 0 && (((uintptr_t)qkv | (uintptr_t)out) & 15) == 0) {
         int rc = pair::launch(qkv, out, B, heads, s);
         if (rc) return rc;
     } else if (L == 50 && !causal) {

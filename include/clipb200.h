@@ -52,6 +52,9 @@ int cb_device_count(int *n);
  *   pdl                0: the towers' kernels are launched without programmatic dependent launch
  *   gemm_skinny        0: single-row-block GEMMs (M <= 128) use the general kernel; 2 / 4 / 8: force a
  *                      cluster split-K of that factor (measured slower than no split; kept for tests)
+ *   gemm_resid_stages  ring depth of the residual-epilogue GEMMs
+ *   attn_tc            0: vision-tower attention runs the mma.sync kernel instead of the tcgen05 kernel that
+ *                      puts two images of a head on one 128-row tile (tests compare the two)
  * Result-corrupting perf probes (gemm_debug, skip) exist only in -DCLIPB200_EXPERIMENTS builds. */
 int cb_tuning_set(const char *name, int64_t value);
 int cb_tuning_get(const char *name, int64_t *value);
