@@ -36,6 +36,17 @@ def available_models() -> List[str]:
     return ["ViT-B/32"]
 
 
+def weights_fingerprint(state_dict) -> str:
+    """Identity of a checkpoint: sha256 over the two projection matrices and the class embedding (fp32 bytes).
+    The indexer stamps it into vectors.lmdb so that rows embedded with different weights (for example the
+    seeded test weights and the real checkpoint) cannot end up in one store unnoticed."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("visual.proj", "visual.class_embedding", "text_projection"):
+        h.update(state_dict[name].detach().to(torch.float32).cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
 class CLIPB200:
     """Duck type of openai/CLIP's `CLIP` module for the two calls the reference makes."""
 
@@ -57,6 +68,7 @@ class CLIPB200:
             N.check(N.lib().cb_clip_set_param(self.handle, name.encode(), C.c_void_p(t.data_ptr()), t.numel()))
         N.check(N.lib().cb_clip_finalize(self.handle))
         self.logit_scale = state_dict.get("logit_scale", torch.tensor(2.6592))
+        self.weights_id = weights_fingerprint(state_dict)
 
     def close(self):
         if getattr(self, "handle", None):

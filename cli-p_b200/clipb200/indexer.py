@@ -155,6 +155,45 @@ class _PilProcessPool:
         self.slots = []
 
 
+META_DB = b"clipb200_meta"      # the reference opens vectors.lmdb with max_dbs=4 and uses three: this is the fourth
+
+
+def check_weights_stamp(env, model) -> None:
+    """vectors.lmdb resumes by key presence (build-index.py:40-42), so rows written with other weights are
+    never recomputed.  The store therefore carries the identity of the checkpoint that filled it
+    (clipb200_meta / b"weights"): a fresh store is stamped, a store stamped by different weights is refused
+    (CLIPB200_ALLOW_MIXED_WEIGHTS=1 overrides), a store without a stamp that already has rows (made by the
+    reference, or by an older clipb200) is left alone."""
+    m = model[0] if isinstance(model, (list, tuple)) else model
+    wid = getattr(m, "weights_id", None)
+    if not wid:
+        return
+    have = None
+    try:
+        meta = env.open_db(META_DB, create=False)
+        with env.begin(db=meta) as txn:
+            have = txn.get(b"weights")
+    except Exception:
+        meta = None                             # no stamp database yet
+    if have is not None:
+        if bytes(have).decode() != wid and os.environ.get("CLIPB200_ALLOW_MIXED_WEIGHTS") != "1":
+            raise RuntimeError(
+                f"vectors.lmdb was filled with CLIP weights {bytes(have).decode()}, this model is {wid}: rows of both would "
+                "mix in one index and resume-by-key would never recompute the old ones. Use a fresh vectors.lmdb "
+                "(or CLIPB200_ALLOW_MIXED_WEIGHTS=1 if you know they are the same model).")
+        return
+    fn_db = env.open_db(b"fn_db")
+    with env.begin(db=fn_db) as txn:
+        empty = txn.stat(fn_db)["entries"] == 0
+    if empty:
+        try:
+            meta = env.open_db(META_DB)
+        except Exception:
+            return                              # max_dbs exhausted or a read-only environment: nothing to record
+        with env.begin(db=meta, write=True) as txn:
+            txn.put(b"weights", wid.encode())
+
+
 def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers: Optional[int] = None,
                   out=sys.stdout, resize: str = "cpu", decode: str = "pil") -> Tuple[int, int]:
     """Embed every new image under `folders` into fn_db.  Returns (embedded, failed).
@@ -166,6 +205,7 @@ def embed_folders(folders: Iterable[str], env, model, batch: int = 256, workers:
     decode="nvjpeg" (implies resize="gpu"): JPEG files are read and decoded a batch per call by
     clipb200.jpeg.Decoder (host threads + nvjpeg behind the C ABI; library work for the decode itself,
     pixels may differ from libjpeg-turbo by +-1); other formats still go through Pillow."""
+    check_weights_stamp(env, model)
     if decode == "nvjpeg" or resize == "gpu" or isinstance(model, (list, tuple)):
         return _embed_folders_gpu_resize(folders, env, model, batch, workers, out, decode)
     fn_db = env.open_db(b"fn_db")

@@ -324,3 +324,31 @@ def test_three_level_tree(tmp_path):
     for key, val, fl in lmdb._walk(memoryview(open(os.path.join(path, "data.mdb"), "rb").read()), meta["main"][7]):
         if key == b"idx_db":
             assert struct.unpack(lmdb.DB_FMT, val)[2] == 3       # depth
+
+
+def test_store_carries_the_identity_of_the_weights_that_filled_it(tmp_path):
+    """A fresh vectors.lmdb is stamped with the checkpoint's fingerprint; another checkpoint is refused
+    (resume-by-key would never recompute the old rows); a store that already has rows but no stamp
+    (the reference's, or an older clipb200's) is left alone."""
+    import types
+
+    import pytest
+    from clipb200 import indexer, lmdb
+    env = lmdb.open(str(tmp_path / "vectors.lmdb"), map_size=1 << 30, max_dbs=4)
+    a, b = types.SimpleNamespace(weights_id="aaaaaaaaaaaaaaaa"), types.SimpleNamespace(weights_id="bbbbbbbbbbbbbbbb")
+    indexer.check_weights_stamp(env, a)
+    with env.begin(db=env.open_db(indexer.META_DB)) as txn:
+        assert bytes(txn.get(b"weights")) == b"aaaaaaaaaaaaaaaa"
+    indexer.check_weights_stamp(env, [a, a])                  # same weights, list of per-GPU models
+    with pytest.raises(RuntimeError, match="fresh vectors.lmdb"):
+        indexer.check_weights_stamp(env, b)
+    env.close()
+
+    env = lmdb.open(str(tmp_path / "old.lmdb"), map_size=1 << 30, max_dbs=4)
+    fn_db = env.open_db(b"fn_db")
+    with env.begin(db=fn_db, write=True) as txn:
+        txn.put(b"x.jpg", b"\0" * 2048)
+    indexer.check_weights_stamp(env, b)                       # unstamped store with rows: not claimed
+    with pytest.raises(lmdb.Error):
+        env.open_db(indexer.META_DB, create=False)            # and nothing was added to it
+    env.close()
