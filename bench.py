@@ -699,8 +699,13 @@ def run_embed(args, torch, dist, rank, world, local):
     secs = timed_region(torch, dist, world, step_dev, args.steps, 0, sampler, drain=join_dev)
     launches = N.launch_count()
     clocks = sampler.stop() if sampler else None
-    # the same metric through the host-buffer API, straight after the device-resident region (same chip state;
-    # the >= 1.2 s sustained region below would otherwise leave it power-capped for a 46 ms e2e region)
+    # the same metric through the host-buffer API, before the >= 1.2 s sustained region below (which would leave
+    # the chip power-capped for a 46 ms region).  A short region is preceded by an idle second, so that it starts
+    # with the power budget the device-resident region started with ~150 ms of load ago; the long default run
+    # needs no such care (both of its regions are sustained)
+    if short_region:
+        torch.cuda.synchronize()
+        time.sleep(1.0)
     e2e_secs = timed_region_wall(torch, dist, world, step_e2e, args.steps, args.warmup, drain=e2e_sync)
     if not short_region:
         roofline = roofline_pass(None)                  # after the long region: the same power-capped state
