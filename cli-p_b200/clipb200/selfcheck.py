@@ -10,6 +10,7 @@ on the user's own weights:
 
   * cosine(libclipb200, fp32 torch) per image / text row -- the north star's bar is >= 0.999;
   * whether cb_clip_finalize kept the LayerNorm fold, and folded vs unfolded agreement;
+  * the tcgen05 attention kernel against the mma.sync one it replaces (knob attn_tc);
   * the largest residual-stream magnitude the fp32 model sees (fp16 overflows at 65504);
   * with --vocab: that clip.tokenize round-trips a few strings through the real merges table.
 
@@ -130,13 +131,17 @@ def main(argv=None) -> int:
         ref = torch.cat([ref_encode_image(sd_dev, imgs[i:i + 16], peak) for i in range(0, len(imgs), 16)])
     got = torch.cat([model.encode_image(imgs[i:i + 64]) for i in range(0, len(imgs), 64)])
     unf = torch.cat([plain.encode_image(imgs[i:i + 64]) for i in range(0, len(imgs), 64)])
+    with N.tuning(attn_tc=0):                      # the mma.sync attention kernel instead of the tcgen05 one
+        alt = torch.cat([model.encode_image(imgs[i:i + 64]) for i in range(0, len(imgs), 64)])
     c = F.cosine_similarity(got, ref)
     cu = F.cosine_similarity(unf, ref)
     cf = F.cosine_similarity(got, unf)
+    ca = F.cosine_similarity(got, alt)
     print(f"encode_image over {len(imgs)} images: cosine vs fp32 torch  min {c.min():.6f}  mean {c.mean():.6f}   "
           f"(unfolded build: min {cu.min():.6f}); shipped vs unfolded min {cf.min():.6f}")
+    print(f"  tcgen05 attention vs mma.sync attention: min cosine {ca.min():.6f}")
     print(f"  largest residual-stream magnitude in the fp32 vision tower: {peak[0]:.1f} (fp16 max 65504)")
-    ok &= bool(c.min() >= args.bar) and peak[0] < 60000
+    ok &= bool(c.min() >= args.bar) and bool(ca.min() >= args.bar) and peak[0] < 60000
 
     if args.vocab:
         os.environ["CLIP_BPE"] = args.vocab
