@@ -182,13 +182,16 @@ attention_kernel(const __half *__restrict__ qkv, __half *__restrict__ out, int h
 // Tile rows: image A tokens at rows 0..49, image B tokens at rows 64..113 (warps 0-1 / 2-3: the TMEM
 // column window a warp reads is warp-uniform).  S[128 x 128] = Q K^T with keys of A in columns 0..63 and
 // keys of B in 64..127: a row reads only its own image's half.  P goes back into tensor memory as fp16,
-// block-diagonal over the 128 keys of both images (the A operand of the second MMA is read from there: the
-// kernel is bound by the 128 B/clk shared-memory port, and P through shared memory was a quarter of its
-// traffic).  O[128 x 64] = P x [V_A ; V_B], V an MN-major operand straight from the row-major TMA image.  The
-// cross terms of S and the zero blocks of P are wasted tensor work (the pipe is idle anyway).  O overwrites
-// S in tensor memory; the fp16 output tile leaves by TMA store.  CTAs are persistent, one per SM, with four
-// independent groups (all 512 tensor-memory columns); per group a fifth warp's elected thread issues every TMA and MMA and fetches the next unit's Q, K as soon as S exists and
-// its V as soon as O does; the row threads and that thread hand over through mbarriers only.
+// block-diagonal over the 128 keys of both images, and is the A operand of the second MMA from there (with
+// P in shared memory the 128 B/clk shared-memory port was ~80 % busy: a quarter of its traffic was P).
+// O[128 x 64] = P x [V_A ; V_B], V an MN-major operand straight from the row-major TMA image.  The cross
+// terms of S and the zero blocks of P are wasted tensor work (about half of the ~900 tensor-pipe clocks per
+// unit; what bounds the kernel is the length of the dependent chain S -> softmax -> PV -> output of each of
+// the four units an SM can hold, not a pipe).  O overwrites S in tensor memory; the fp16 output tile leaves
+// by TMA store.  CTAs are persistent, one per SM, with four independent groups (all 512 tensor-memory
+// columns); per group a fifth warp's elected thread issues every TMA and MMA and fetches the next unit's
+// Q, K as soon as S exists and its V as soon as the output tile has left; the row threads and that thread
+// hand over through mbarriers only.
 namespace pair {
 using namespace tc;
 constexpr int L = 50;
